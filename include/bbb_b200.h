@@ -1,0 +1,167 @@
+/*
+ * bbb_b200.h -- C ABI of the B200-native Bayes-by-Backprop layer engine.
+ *
+ * The reference (kumar-shridhar/PyTorch-BayesianCNN) has no FFI / plugin layer:
+ * its boundary for this path is the Python class surface of layers/ (SURVEY.md
+ * 8b).  Each entry point below replaces the body of one reference method; the
+ * Python host side (pytorch_bayesiancnn_b200/) keeps the reference's class and
+ * argument names and calls these through ctypes (see INTEGRATION.md for the
+ * stub a maintainer of the reference would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch types.  All pointers are DEVICE
+ *     pointers unless the name ends in _host.  `cuda_stream` is a cudaStream_t
+ *     (CUstream) handle passed as void*; every call is asynchronous on it and
+ *     never synchronises, allocates or takes ownership.
+ *   - parameters are fp32, reference layout: W_mu/W_rho [Cout, Cin, kh, kw]
+ *     (OIHW) or [out, in]; bias_mu/bias_rho [Cout].  Activations are logical
+ *     NCHW, contiguous.
+ *   - return 0 on success, a negative BBB_E_* code on error;
+ *     bbb_last_error() gives the message (thread-local).
+ *   - noise: eps pointers NULL  => in-kernel Philox4x32-10 keyed by
+ *     (seed, stream_id, flat element index) -- see bbb_philox_normal_fill for
+ *     the exact stream definition; non-NULL => that tensor is used (parity mode,
+ *     identical eps to the reference's CPU-generator draws).
+ */
+#ifndef BBB_B200_H_
+#define BBB_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BBB_ABI_VERSION 1
+
+enum { BBB_VARIANT_BBB = 0,   /* weight-space sampling   (layers/BBB/...)      */
+       BBB_VARIANT_LRT = 1 }; /* local reparameterisation (layers/BBB_LRT/...) */
+enum { BBB_DTYPE_F32 = 0, BBB_DTYPE_BF16 = 1 };
+enum { BBB_MATH_FP32 = 0,      /* CUDA-core FFMA, IEEE fp32 accumulate          */
+       BBB_MATH_BF16_TC = 1,   /* tcgen05 bf16 x bf16 -> fp32 in TMEM           */
+       BBB_MATH_AUTO = 2 };    /* engine picks per layer shape                  */
+enum { BBB_KL_REFERENCE = 0,   /* as executed by the reference: KL(prior||post) */
+       BBB_KL_TEXTBOOK = 1 };  /* KL(q||p)                                      */
+enum { BBB_ACT_NONE = 0, BBB_ACT_SOFTPLUS = 1, BBB_ACT_RELU = 2 };
+
+enum { BBB_OK = 0, BBB_E_INVALID = -1, BBB_E_UNSUPPORTED = -2, BBB_E_WORKSPACE = -3,
+       BBB_E_CUDA = -4 };
+
+/* Geometry + options of one Bayesian layer call.  A linear layer is the
+ * degenerate conv: in_h = in_w = kernel = stride = dil = 1, pad = 0,
+ * in_channels = in_features, out_channels = out_features, batch = rows. */
+typedef struct bbb_layer_desc {
+    int32_t batch;
+    int32_t in_channels, in_h, in_w;
+    int32_t out_channels;
+    int32_t kernel_h, kernel_w;
+    int32_t stride_h, stride_w;
+    int32_t pad_h, pad_w;
+    int32_t dil_h, dil_w;
+    int32_t variant;        /* BBB_VARIANT_*                                          */
+    int32_t sample;         /* 1: stochastic (self.training or sample); 0: mean only */
+    int32_t has_bias;
+    int32_t act_dtype;      /* BBB_DTYPE_*: dtype of x and y                          */
+    int32_t math;           /* BBB_MATH_*                                             */
+    int32_t kl_convention;  /* BBB_KL_*                                               */
+    int32_t epilogue_act;   /* BBB_ACT_*: activation fused after the layer (0 = none) */
+    int32_t pool_k, pool_s; /* max-pool fused after the activation (0 = none)         */
+    int32_t reserved[4];
+    float prior_mu, prior_sigma;
+} bbb_layer_desc;
+
+/* Bytes of caller-allocated scratch a forward/KL call on `desc` needs.  The
+ * scratch must be zero-filled ONCE when allocated; calls leave it zeroed where
+ * that matters (self-resetting counters). */
+size_t bbb_workspace_bytes(const bbb_layer_desc* desc);
+
+/* Replaces BBBConv2d.forward + .kl_loss:
+ *   layers/BBB/BBBConv.py:61-83, layers/BBB_LRT/BBBConv.py:62-87.
+ * y      : [batch, out_channels, OH, OW]
+ * kl_out : nullable; the layer's KL scalar (weights + bias) is WRITTEN here.
+ * act_std: nullable, LRT only, fp32 shape of y: sqrt(act_var) (BBB_LRT/BBBConv.py:75)
+ *          saved for the backward.
+ * eps_a  : BBB: W_eps [Cout,Cin,kh,kw]; LRT: activation eps, shape of y.  NULL => Philox.
+ * eps_b  : BBB: bias_eps [Cout]; LRT: unused.                             NULL => Philox.
+ * Philox element index: BBB: flat OIHW index for W, |W| + c for bias;
+ *                       LRT: flat NCHW index of y.                                    */
+int bbb_conv2d_forward(const bbb_layer_desc* desc, const void* x,
+                       const float* W_mu, const float* W_rho,
+                       const float* bias_mu, const float* bias_rho,
+                       void* y, float* kl_out, float* act_std,
+                       const float* eps_a, const float* eps_b,
+                       uint64_t seed, uint64_t stream_id,
+                       void* workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* Replaces BBBLinear.forward + .kl_loss:
+ *   layers/BBB/BBBLinear.py:54-76, layers/BBB_LRT/BBBLinear.py:56-79.
+ * Same arguments; desc must be the degenerate (1x1) geometry. */
+int bbb_linear_forward(const bbb_layer_desc* desc, const void* x,
+                       const float* W_mu, const float* W_rho,
+                       const float* bias_mu, const float* bias_rho,
+                       void* y, float* kl_out, float* act_std,
+                       const float* eps_a, const float* eps_b,
+                       uint64_t seed, uint64_t stream_id,
+                       void* workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* Replaces layer.kl_loss() -> metrics.calculate_kl (metrics.py:27-29 with the call
+ * binding of layers/BBB/BBBConv.py:80-82) when no forward preceded it: sigma is
+ * recomputed from rho.  n_w = |W|, n_b = |bias| (0 if none). */
+int bbb_kl_forward(const float* W_mu, const float* W_rho, uint64_t n_w,
+                   const float* bias_mu, const float* bias_rho, uint64_t n_b,
+                   float prior_mu, float prior_sigma, int32_t kl_convention,
+                   float* kl_out, void* workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* d(kl)/d(mu), d(kl)/d(rho), scaled by *grad_kl (device scalar) and ACCUMULATED
+ * into g_mu / g_rho. */
+int bbb_kl_backward(const float* mu, const float* rho, uint64_t n,
+                    float prior_mu, float prior_sigma, int32_t kl_convention,
+                    const float* grad_kl, float* g_mu, float* g_rho, void* cuda_stream);
+
+/* Backward of bbb_conv2d_forward / bbb_linear_forward.
+ * Regenerates eps from (seed, stream_id) or reads eps_a/eps_b exactly like the
+ * forward.  grad_x nullable.  g_* are ACCUMULATED into (caller zeroes).
+ * act_std: LRT only, the tensor the forward saved.                            */
+int bbb_conv2d_backward(const bbb_layer_desc* desc, const void* x, const void* grad_y,
+                        const float* W_mu, const float* W_rho,
+                        const float* bias_mu, const float* bias_rho,
+                        const float* act_std,
+                        const float* eps_a, const float* eps_b,
+                        uint64_t seed, uint64_t stream_id,
+                        void* grad_x, float* g_W_mu, float* g_W_rho,
+                        float* g_bias_mu, float* g_bias_rho,
+                        void* workspace, size_t workspace_bytes, void* cuda_stream);
+int bbb_linear_backward(const bbb_layer_desc* desc, const void* x, const void* grad_y,
+                        const float* W_mu, const float* W_rho,
+                        const float* bias_mu, const float* bias_rho,
+                        const float* act_std,
+                        const float* eps_a, const float* eps_b,
+                        uint64_t seed, uint64_t stream_id,
+                        void* grad_x, float* g_W_mu, float* g_W_rho,
+                        float* g_bias_mu, float* g_bias_rho,
+                        void* workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* The engine's noise stream, exposed so the host side of the boundary can draw
+ * exactly what a kernel draws: out[i] = N(0,1) lane ((offset+i)&3) of
+ * Philox4x32-10(counter = ((offset+i)>>2, stream_id), key = seed), Box-Muller. */
+int bbb_philox_normal_fill(float* out, uint64_t n, uint64_t seed, uint64_t stream_id,
+                           uint64_t offset, void* cuda_stream);
+
+/* Monte-Carlo combine that sits directly above the path (main_bayesian.py:46-53,
+ * utils.py:14-22): logits [S, B, C] fp32 -> log_outputs [B, C] =
+ * logmeanexp_s(log_softmax(logits[s])).  Also emits per-sample partials
+ * (sum_s softmax, sum_s softmax^2, sum_s logits) [3, B, C] if `moments` != NULL
+ * (uncertainty_estimation.py:70-96). */
+int bbb_mc_combine(const float* logits, int32_t S, int32_t B, int32_t C,
+                   float* log_outputs, float* moments, void* cuda_stream);
+
+const char* bbb_last_error(void);
+int32_t bbb_abi_version(void);
+/* Number of kernels this library has launched since load (all entry points). */
+uint64_t bbb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* BBB_B200_H_ */

@@ -1,0 +1,237 @@
+// C-ABI entry points of libbbb_b200.so (declared in include/bbb_b200.h).
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+#include "fwd_simt.cuh"
+#include "misc_kernels.cuh"
+#include "bwd_simt.cuh"
+#include "fwd_tc.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    return fail(BBB_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+constexpr size_t kCounterBytes = 64;
+constexpr size_t kMaxKlSlots = 4096;
+constexpr size_t kBaseWorkspace = kCounterBytes + kMaxKlSlots * sizeof(double);
+
+int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0; cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+int check_desc(const bbb_layer_desc* d, bbb::Geom& g, bool linear) {
+    if (!d) return fail(BBB_E_INVALID, "desc is NULL");
+    if (!bbb::make_geom(*d, g)) return fail(BBB_E_INVALID, "invalid layer geometry");
+    if (linear && !g.linear_like) return fail(BBB_E_INVALID, "bbb_linear_*: desc is not the degenerate 1x1 geometry");
+    if (d->variant != BBB_VARIANT_BBB && d->variant != BBB_VARIANT_LRT) return fail(BBB_E_INVALID, "bad variant %d", d->variant);
+    if (d->kl_convention != BBB_KL_REFERENCE && d->kl_convention != BBB_KL_TEXTBOOK) return fail(BBB_E_INVALID, "bad kl_convention");
+    if (d->epilogue_act < BBB_ACT_NONE || d->epilogue_act > BBB_ACT_RELU) return fail(BBB_E_INVALID, "bad epilogue_act");
+    if (!(d->prior_sigma > 0.0f)) return fail(BBB_E_INVALID, "prior_sigma must be > 0");
+    return BBB_OK;
+}
+
+int forward_impl(const bbb_layer_desc* d, bool linear, const void* x, const float* W_mu, const float* W_rho,
+                 const float* bias_mu, const float* bias_rho, void* y, float* kl_out, float* act_std,
+                 const float* eps_a, const float* eps_b, uint64_t seed, uint64_t stream_id, void* ws,
+                 size_t ws_bytes, void* stream) {
+    bbb::Geom g;
+    if (int rc = check_desc(d, g, linear)) return rc;
+    if (!x || !W_mu || !W_rho || !y) return fail(BBB_E_INVALID, "NULL tensor pointer");
+    if (d->has_bias && (!bias_mu || !bias_rho)) return fail(BBB_E_INVALID, "has_bias set but bias pointers NULL");
+    if (kl_out && (!ws || ws_bytes < bbb_workspace_bytes(d)))
+        return fail(BBB_E_WORKSPACE, "workspace too small: need %zu bytes", bbb_workspace_bytes(d));
+    if (d->pool_k != 0) return fail(BBB_E_UNSUPPORTED, "fused max-pool epilogue is not available on this path");
+    cudaStream_t st = (cudaStream_t)stream;
+
+    int math = d->math;
+    if (math == BBB_MATH_AUTO) math = bbb::tc_supported(*d, g) ? BBB_MATH_BF16_TC : BBB_MATH_FP32;
+    if (math == BBB_MATH_BF16_TC) {
+        if (!bbb::tc_supported(*d, g)) return fail(BBB_E_UNSUPPORTED, "BBB_MATH_BF16_TC: shape not supported by the tcgen05 path");
+        bbb::TcArgs a;
+        a.g = g; a.x = x; a.w_mu = W_mu; a.w_rho = W_rho; a.b_mu = bias_mu; a.b_rho = bias_rho;
+        a.y = y; a.kl_out = kl_out; a.act_std = act_std; a.eps_a = eps_a; a.eps_b = eps_b;
+        a.key = bbb::make_key(seed, stream_id);
+        a.kl_counter = (unsigned int*)ws; a.kl_partials = (double*)((char*)ws + kCounterBytes);
+        a.prior_mu = d->prior_mu; a.prior_sigma = d->prior_sigma;
+        a.sample = d->sample; a.kl_convention = d->kl_convention; a.has_bias = d->has_bias; a.act = d->epilogue_act;
+        a.act_dtype = d->act_dtype; a.variant = d->variant;
+        int nl = 0;
+        cudaError_t e = bbb::launch_fwd_tc(a, st, sm_count(), &nl);
+        if (e != cudaSuccess) return cuda_fail(e, "fwd_tc launch");
+        g_launches += nl;
+        return BBB_OK;
+    }
+    if (math != BBB_MATH_FP32) return fail(BBB_E_INVALID, "bad math mode %d", d->math);
+    if (d->act_dtype != BBB_DTYPE_F32) return fail(BBB_E_UNSUPPORTED, "BBB_MATH_FP32 path takes fp32 activations only");
+
+    bbb::FwdArgs a;
+    a.g = g; a.x = (const float*)x; a.w_mu = W_mu; a.w_rho = W_rho; a.b_mu = bias_mu; a.b_rho = bias_rho;
+    a.y = (float*)y; a.kl_out = kl_out; a.act_std = act_std; a.eps_a = eps_a; a.eps_b = eps_b;
+    a.key = bbb::make_key(seed, stream_id);
+    a.kl_counter = (unsigned int*)ws; a.kl_partials = (double*)((char*)ws + kCounterBytes);
+    a.prior_mu = d->prior_mu; a.prior_sigma = d->prior_sigma;
+    a.sample = d->sample; a.kl_convention = d->kl_convention; a.has_bias = d->has_bias; a.act = d->epilogue_act;
+    cudaError_t e = d->variant == BBB_VARIANT_LRT ? bbb::launch_fwd_simt<BBB_VARIANT_LRT>(a, st)
+                                                  : bbb::launch_fwd_simt<BBB_VARIANT_BBB>(a, st);
+    if (e != cudaSuccess) return cuda_fail(e, "fwd_simt launch");
+    g_launches += 1;
+    return BBB_OK;
+}
+
+int backward_impl(const bbb_layer_desc* d, bool linear, const void* x, const void* grad_y, const float* W_mu,
+                  const float* W_rho, const float* bias_mu, const float* bias_rho, const float* act_std,
+                  const float* eps_a, const float* eps_b, uint64_t seed, uint64_t stream_id, void* grad_x,
+                  float* g_W_mu, float* g_W_rho, float* g_bias_mu, float* g_bias_rho, void* ws, size_t ws_bytes,
+                  void* stream) {
+    bbb::Geom g;
+    if (int rc = check_desc(d, g, linear)) return rc;
+    if (!x || !grad_y || !W_mu || !W_rho) return fail(BBB_E_INVALID, "NULL tensor pointer");
+    if (d->act_dtype != BBB_DTYPE_F32) return fail(BBB_E_UNSUPPORTED, "backward takes fp32 activations only");
+    if (d->epilogue_act != BBB_ACT_NONE || d->pool_k != 0)
+        return fail(BBB_E_UNSUPPORTED, "backward through a fused activation/pool epilogue is not available");
+    if (d->variant == BBB_VARIANT_LRT && d->sample && !act_std)
+        return fail(BBB_E_INVALID, "LRT backward needs the act_std tensor saved by the forward");
+    (void)ws; (void)ws_bytes;
+    bbb::BwdArgs a;
+    a.g = g; a.x = (const float*)x; a.gy = (const float*)grad_y; a.w_mu = W_mu; a.w_rho = W_rho;
+    a.b_mu = bias_mu; a.b_rho = bias_rho; a.act_std = act_std; a.eps_a = eps_a; a.eps_b = eps_b;
+    a.key = bbb::make_key(seed, stream_id);
+    a.gx = (float*)grad_x; a.g_w_mu = g_W_mu; a.g_w_rho = g_W_rho; a.g_b_mu = g_bias_mu; a.g_b_rho = g_bias_rho;
+    a.sample = d->sample; a.has_bias = d->has_bias; a.variant = d->variant;
+    int nl = 0;
+    cudaError_t e = bbb::launch_bwd_simt(a, (cudaStream_t)stream, sm_count(), &nl);
+    if (e != cudaSuccess) return cuda_fail(e, "bwd_simt launch");
+    g_launches += nl;
+    return BBB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t bbb_workspace_bytes(const bbb_layer_desc* desc) {
+    (void)desc;
+    return kBaseWorkspace;
+}
+
+int bbb_conv2d_forward(const bbb_layer_desc* desc, const void* x, const float* W_mu, const float* W_rho,
+                       const float* bias_mu, const float* bias_rho, void* y, float* kl_out, float* act_std,
+                       const float* eps_a, const float* eps_b, uint64_t seed, uint64_t stream_id,
+                       void* workspace, size_t workspace_bytes, void* cuda_stream) {
+    return forward_impl(desc, false, x, W_mu, W_rho, bias_mu, bias_rho, y, kl_out, act_std, eps_a, eps_b, seed,
+                        stream_id, workspace, workspace_bytes, cuda_stream);
+}
+
+int bbb_linear_forward(const bbb_layer_desc* desc, const void* x, const float* W_mu, const float* W_rho,
+                       const float* bias_mu, const float* bias_rho, void* y, float* kl_out, float* act_std,
+                       const float* eps_a, const float* eps_b, uint64_t seed, uint64_t stream_id,
+                       void* workspace, size_t workspace_bytes, void* cuda_stream) {
+    return forward_impl(desc, true, x, W_mu, W_rho, bias_mu, bias_rho, y, kl_out, act_std, eps_a, eps_b, seed,
+                        stream_id, workspace, workspace_bytes, cuda_stream);
+}
+
+int bbb_conv2d_backward(const bbb_layer_desc* desc, const void* x, const void* grad_y, const float* W_mu,
+                        const float* W_rho, const float* bias_mu, const float* bias_rho, const float* act_std,
+                        const float* eps_a, const float* eps_b, uint64_t seed, uint64_t stream_id, void* grad_x,
+                        float* g_W_mu, float* g_W_rho, float* g_bias_mu, float* g_bias_rho, void* workspace,
+                        size_t workspace_bytes, void* cuda_stream) {
+    return backward_impl(desc, false, x, grad_y, W_mu, W_rho, bias_mu, bias_rho, act_std, eps_a, eps_b, seed,
+                         stream_id, grad_x, g_W_mu, g_W_rho, g_bias_mu, g_bias_rho, workspace, workspace_bytes,
+                         cuda_stream);
+}
+
+int bbb_linear_backward(const bbb_layer_desc* desc, const void* x, const void* grad_y, const float* W_mu,
+                        const float* W_rho, const float* bias_mu, const float* bias_rho, const float* act_std,
+                        const float* eps_a, const float* eps_b, uint64_t seed, uint64_t stream_id, void* grad_x,
+                        float* g_W_mu, float* g_W_rho, float* g_bias_mu, float* g_bias_rho, void* workspace,
+                        size_t workspace_bytes, void* cuda_stream) {
+    return backward_impl(desc, true, x, grad_y, W_mu, W_rho, bias_mu, bias_rho, act_std, eps_a, eps_b, seed,
+                         stream_id, grad_x, g_W_mu, g_W_rho, g_bias_mu, g_bias_rho, workspace, workspace_bytes,
+                         cuda_stream);
+}
+
+int bbb_kl_forward(const float* W_mu, const float* W_rho, uint64_t n_w, const float* bias_mu,
+                   const float* bias_rho, uint64_t n_b, float prior_mu, float prior_sigma, int32_t kl_convention,
+                   float* kl_out, void* workspace, size_t workspace_bytes, void* cuda_stream) {
+    if (!W_mu || !W_rho || !kl_out) return fail(BBB_E_INVALID, "NULL tensor pointer");
+    if (n_b && (!bias_mu || !bias_rho)) return fail(BBB_E_INVALID, "n_b > 0 but bias pointers NULL");
+    if (!workspace || workspace_bytes < kBaseWorkspace) return fail(BBB_E_WORKSPACE, "workspace too small: need %zu bytes", kBaseWorkspace);
+    if (!(prior_sigma > 0.0f)) return fail(BBB_E_INVALID, "prior_sigma must be > 0");
+    const uint64_t work = (n_w + 3) / 4 + n_b;
+    uint64_t blocks = (work + 255) / 256;
+    const uint64_t cap = (uint64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    if (blocks > kMaxKlSlots) blocks = kMaxKlSlots;
+    bbb::kl_forward_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)cuda_stream>>>(
+        W_mu, W_rho, n_w, bias_mu, bias_rho, n_b, prior_mu, prior_sigma, kl_convention,
+        (double*)((char*)workspace + kCounterBytes), (unsigned int*)workspace, kl_out);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "kl_forward launch");
+    g_launches += 1;
+    return BBB_OK;
+}
+
+int bbb_kl_backward(const float* mu, const float* rho, uint64_t n, float prior_mu, float prior_sigma,
+                    int32_t kl_convention, const float* grad_kl, float* g_mu, float* g_rho, void* cuda_stream) {
+    if (!mu || !rho || !grad_kl || !g_mu || !g_rho) return fail(BBB_E_INVALID, "NULL tensor pointer");
+    if (n == 0) return BBB_OK;
+    uint64_t blocks = (n + 255) / 256;
+    const uint64_t cap = (uint64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    bbb::kl_backward_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)cuda_stream>>>(
+        mu, rho, n, prior_mu, prior_sigma, kl_convention, grad_kl, g_mu, g_rho);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "kl_backward launch");
+    g_launches += 1;
+    return BBB_OK;
+}
+
+int bbb_philox_normal_fill(float* out, uint64_t n, uint64_t seed, uint64_t stream_id, uint64_t offset,
+                           void* cuda_stream) {
+    if (!out) return fail(BBB_E_INVALID, "NULL output pointer");
+    if (n == 0) return BBB_OK;
+    uint64_t blocks = (n + 255) / 256;
+    const uint64_t cap = (uint64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    bbb::philox_fill_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)cuda_stream>>>(out, n, bbb::make_key(seed, stream_id), offset);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "philox_fill launch");
+    g_launches += 1;
+    return BBB_OK;
+}
+
+int bbb_mc_combine(const float* logits, int32_t S, int32_t B, int32_t C, float* log_outputs, float* moments,
+                   void* cuda_stream) {
+    if (!logits || !log_outputs) return fail(BBB_E_INVALID, "NULL tensor pointer");
+    if (S <= 0 || B <= 0 || C <= 0) return fail(BBB_E_INVALID, "bad S/B/C");
+    if ((size_t)S * sizeof(float) > 40000) return fail(BBB_E_UNSUPPORTED, "S too large");
+    bbb::mc_combine_kernel<<<B, 128, S * sizeof(float), (cudaStream_t)cuda_stream>>>(logits, S, B, C, log_outputs, moments);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "mc_combine launch");
+    g_launches += 1;
+    return BBB_OK;
+}
+
+const char* bbb_last_error(void) { return g_err; }
+int32_t bbb_abi_version(void) { return BBB_ABI_VERSION; }
+uint64_t bbb_launch_count(void) { return g_launches.load(); }
+
+}  // extern "C"

@@ -1,0 +1,307 @@
+"""Host side of the boundary: torch.autograd.Functions that call the C ABI.
+
+PyTorch supplies device memory, the current stream and autograd; every number on
+the Bayesian layer path is produced by libbbb_b200.so.  Nothing here computes a
+layer with aten ops.
+"""
+from __future__ import annotations
+
+import contextlib
+import ctypes as C
+import threading
+from typing import Iterable, Optional
+
+import torch
+
+from . import _lib as L
+
+
+# --------------------------------------------------------------------------- #
+# noise bookkeeping (Python owns (seed, stream_id); kernels own the draws)
+# --------------------------------------------------------------------------- #
+class _Noise(threading.local):
+    def __init__(self):
+        self.seed = 0x5EEDB200
+        self.counter = 0
+        self.queue = None          # external-eps queue (parity mode)
+
+
+_noise = _Noise()
+
+
+def manual_seed(seed: int, counter: int = 0):
+    """Seed the engine's Philox streams.  Every stochastic layer call consumes one
+    stream id (counter += 1), so a fixed seed replays the same noise."""
+    _noise.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    _noise.counter = int(counter)
+
+
+def begin_sample(sample_id: int):
+    """Position the stream counter for Monte-Carlo sample `sample_id` (global id):
+    layer calls of that sample use stream ids (sample_id << 32) + 0, 1, 2, ...  so
+    results do not depend on how samples are sharded over ranks."""
+    _noise.counter = int(sample_id) << 32
+
+
+def next_stream() -> tuple[int, int]:
+    s = _noise.counter
+    _noise.counter += 1
+    return _noise.seed, s
+
+
+@contextlib.contextmanager
+def external_eps(tensors: Iterable[torch.Tensor]):
+    """Parity mode: feed the layers the eps tensors the reference drew, in the
+    reference's draw order (BBB: W_eps then bias_eps per layer -- BBB/BBBConv.py:63,68;
+    LRT: one activation-shaped eps per layer -- BBB_LRT/BBBConv.py:78)."""
+    prev = _noise.queue
+    _noise.queue = list(tensors)
+    try:
+        yield
+        if _noise.queue:
+            raise RuntimeError(f"external_eps: {len(_noise.queue)} eps tensors were not consumed")
+    finally:
+        _noise.queue = prev
+
+
+def _pop_eps(shape, device):
+    q = _noise.queue
+    if q is None:
+        return None
+    if not q:
+        raise RuntimeError("external_eps: queue exhausted")
+    e = q.pop(0)
+    if tuple(e.shape) != tuple(shape):
+        raise RuntimeError(f"external_eps: expected shape {tuple(shape)}, got {tuple(e.shape)}")
+    return e.to(device=device, dtype=torch.float32).contiguous()
+
+
+def external_eps_active() -> bool:
+    return _noise.queue is not None
+
+
+# --------------------------------------------------------------------------- #
+# helpers
+# --------------------------------------------------------------------------- #
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise L.EngineError(
+            f"{what}: tensor is on {t.device}; the Bayesian layer engine runs on CUDA (sm_100a) only "
+            "and has no CPU fallback")
+
+
+_ws_cache: dict = {}
+
+
+def workspace(device) -> torch.Tensor:
+    """Zero-initialised scratch, one per (device, stream): calls on one stream are
+    ordered, so sharing it is safe; the kernels leave it zeroed."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None:
+        n = int(L.lib().bbb_workspace_bytes(None))
+        ws = torch.zeros(n, dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def make_desc(x_shape, w_shape, conv, variant, sample, has_bias, prior_mu, prior_sigma,
+              math=L.MATH_FP32, kl_convention=L.KL_REFERENCE, act=L.ACT_NONE,
+              act_dtype=L.DTYPE_F32) -> L.LayerDesc:
+    d = L.LayerDesc()
+    if conv is None:
+        d.batch, d.in_channels, d.in_h, d.in_w = x_shape[0], x_shape[1], 1, 1
+        d.out_channels, d.kernel_h, d.kernel_w = w_shape[0], 1, 1
+        d.stride_h = d.stride_w = d.dil_h = d.dil_w = 1
+        d.pad_h = d.pad_w = 0
+    else:
+        (sh, sw), (ph, pw), (dh, dw) = conv
+        d.batch, d.in_channels, d.in_h, d.in_w = x_shape
+        d.out_channels, _, d.kernel_h, d.kernel_w = w_shape
+        d.stride_h, d.stride_w, d.pad_h, d.pad_w, d.dil_h, d.dil_w = sh, sw, ph, pw, dh, dw
+    d.variant, d.sample, d.has_bias = variant, int(bool(sample)), int(bool(has_bias))
+    d.act_dtype, d.math, d.kl_convention, d.epilogue_act = act_dtype, math, kl_convention, act
+    d.pool_k = d.pool_s = 0
+    d.prior_mu, d.prior_sigma = float(prior_mu), float(prior_sigma)
+    return d
+
+
+def out_hw(h, w, kh, kw, conv):
+    (sh, sw), (ph, pw), (dh, dw) = conv
+    return ((h + 2 * ph - dh * (kh - 1) - 1) // sh + 1, (w + 2 * pw - dw * (kw - 1) - 1) // sw + 1)
+
+
+# --------------------------------------------------------------------------- #
+# the layer op
+# --------------------------------------------------------------------------- #
+class BayesLayerFn(torch.autograd.Function):
+    """(y, kl) = layer(x; W_mu, W_rho, bias_mu, bias_rho).  One fused kernel forward;
+    backward = bbb_*_backward + bbb_kl_backward accumulating into the same grads."""
+
+    @staticmethod
+    def forward(ctx, x, W_mu, W_rho, bias_mu, bias_rho, cfg):
+        lib = L.lib()
+        _require_cuda(x, "BayesLayerFn")
+        _require_cuda(W_mu, "BayesLayerFn (parameters)")
+        dev = x.device
+        conv = cfg["conv"]
+        variant, sample = cfg["variant"], cfg["sample"]
+        x = x.contiguous()
+        if x.dtype != torch.float32:
+            x = x.float()
+        W_mu_c, W_rho_c = W_mu.contiguous(), W_rho.contiguous()
+        has_bias = bias_mu is not None
+        d = make_desc(tuple(x.shape), tuple(W_mu.shape), conv, variant, sample, has_bias,
+                      cfg["prior_mu"], cfg["prior_sigma"], cfg["math"], cfg["kl_convention"], cfg["act"])
+        if conv is None:
+            if x.dim() != 2 or x.shape[1] != W_mu.shape[1]:
+                raise L.EngineError(f"linear: x {tuple(x.shape)} vs weight {tuple(W_mu.shape)}")
+            yshape = (x.shape[0], W_mu.shape[0])
+        else:
+            if x.dim() != 4 or x.shape[1] != W_mu.shape[1]:
+                raise L.EngineError(f"conv2d: x {tuple(x.shape)} vs weight {tuple(W_mu.shape)}")
+            oh, ow = out_hw(x.shape[2], x.shape[3], W_mu.shape[2], W_mu.shape[3], conv)
+            yshape = (x.shape[0], W_mu.shape[0], oh, ow)
+        y = torch.empty(yshape, dtype=torch.float32, device=dev)
+        kl = torch.empty((), dtype=torch.float32, device=dev)
+        eps_a = eps_b = None
+        seed = stream_id = 0
+        if sample:
+            if external_eps_active():
+                if variant == L.VARIANT_BBB:
+                    eps_a = _pop_eps(W_mu.shape, dev)
+                    if has_bias:
+                        eps_b = _pop_eps(bias_mu.shape, dev)
+                else:
+                    eps_a = _pop_eps(yshape, dev)
+            else:
+                seed, stream_id = next_stream()
+        need_grad = any(ctx.needs_input_grad[:5])      # grad mode is off inside Function.forward
+        act_std = None
+        if variant == L.VARIANT_LRT and sample and need_grad:
+            act_std = torch.empty(yshape, dtype=torch.float32, device=dev)
+        ws = workspace(dev)
+        fn = lib.bbb_linear_forward if conv is None else lib.bbb_conv2d_forward
+        rc = fn(C.byref(d), _ptr(x), _ptr(W_mu_c), _ptr(W_rho_c), _ptr(bias_mu), _ptr(bias_rho),
+                _ptr(y), _ptr(kl), _ptr(act_std), _ptr(eps_a), _ptr(eps_b),
+                C.c_uint64(seed), C.c_uint64(stream_id), _ptr(ws), C.c_size_t(ws.numel()), _stream(dev))
+        L.check(rc, "bbb_linear_forward" if conv is None else "bbb_conv2d_forward")
+        ctx.cfg = cfg
+        ctx.desc = d
+        ctx.noise = (seed, stream_id)
+        ctx.has_bias = has_bias
+        ctx.save_for_backward(x, W_mu_c, W_rho_c, bias_mu, bias_rho, act_std, eps_a, eps_b)
+        return y, kl
+
+    @staticmethod
+    def backward(ctx, gy, gkl):
+        lib = L.lib()
+        x, W_mu, W_rho, bias_mu, bias_rho, act_std, eps_a, eps_b = ctx.saved_tensors
+        cfg, d = ctx.cfg, ctx.desc
+        dev = x.device
+        if cfg["act"] != L.ACT_NONE:
+            raise L.EngineError("backward through a fused activation epilogue is not available")
+        g_W_mu = torch.zeros_like(W_mu)
+        g_W_rho = torch.zeros_like(W_rho)
+        g_b_mu = torch.zeros_like(bias_mu) if ctx.has_bias else None
+        g_b_rho = torch.zeros_like(bias_rho) if ctx.has_bias else None
+        gx = None
+        if gy is not None:
+            gy = gy.contiguous().float()
+            if ctx.needs_input_grad[0]:
+                gx = torch.zeros_like(x)
+            ws = workspace(dev)
+            fn = lib.bbb_linear_backward if cfg["conv"] is None else lib.bbb_conv2d_backward
+            seed, stream_id = ctx.noise
+            rc = fn(C.byref(d), _ptr(x), _ptr(gy), _ptr(W_mu), _ptr(W_rho), _ptr(bias_mu), _ptr(bias_rho),
+                    _ptr(act_std), _ptr(eps_a), _ptr(eps_b), C.c_uint64(seed), C.c_uint64(stream_id),
+                    _ptr(gx), _ptr(g_W_mu), _ptr(g_W_rho), _ptr(g_b_mu), _ptr(g_b_rho),
+                    _ptr(ws), C.c_size_t(ws.numel()), _stream(dev))
+            L.check(rc, "bbb_*_backward")
+        if gkl is not None:
+            gkl = gkl.contiguous().float()
+            rc = lib.bbb_kl_backward(_ptr(W_mu), _ptr(W_rho), C.c_uint64(W_mu.numel()),
+                                     C.c_float(cfg["prior_mu"]), C.c_float(cfg["prior_sigma"]),
+                                     C.c_int32(cfg["kl_convention"]), _ptr(gkl), _ptr(g_W_mu), _ptr(g_W_rho),
+                                     _stream(dev))
+            L.check(rc, "bbb_kl_backward")
+            if ctx.has_bias:
+                rc = lib.bbb_kl_backward(_ptr(bias_mu), _ptr(bias_rho), C.c_uint64(bias_mu.numel()),
+                                         C.c_float(cfg["prior_mu"]), C.c_float(cfg["prior_sigma"]),
+                                         C.c_int32(cfg["kl_convention"]), _ptr(gkl), _ptr(g_b_mu), _ptr(g_b_rho),
+                                         _stream(dev))
+                L.check(rc, "bbb_kl_backward")
+        return gx, g_W_mu, g_W_rho, g_b_mu, g_b_rho, None
+
+
+class KLFn(torch.autograd.Function):
+    """kl_loss() with no preceding forward: sigma recomputed from rho in the kernel."""
+
+    @staticmethod
+    def forward(ctx, W_mu, W_rho, bias_mu, bias_rho, prior_mu, prior_sigma, kl_convention):
+        lib = L.lib()
+        _require_cuda(W_mu, "kl_loss")
+        dev = W_mu.device
+        W_mu_c, W_rho_c = W_mu.contiguous(), W_rho.contiguous()
+        kl = torch.empty((), dtype=torch.float32, device=dev)
+        ws = workspace(dev)
+        nb = 0 if bias_mu is None else bias_mu.numel()
+        rc = lib.bbb_kl_forward(_ptr(W_mu_c), _ptr(W_rho_c), C.c_uint64(W_mu.numel()), _ptr(bias_mu), _ptr(bias_rho),
+                                C.c_uint64(nb), C.c_float(prior_mu), C.c_float(prior_sigma), C.c_int32(kl_convention),
+                                _ptr(kl), _ptr(ws), C.c_size_t(ws.numel()), _stream(dev))
+        L.check(rc, "bbb_kl_forward")
+        ctx.save_for_backward(W_mu_c, W_rho_c, bias_mu, bias_rho)
+        ctx.cfg = (float(prior_mu), float(prior_sigma), int(kl_convention))
+        return kl
+
+    @staticmethod
+    def backward(ctx, gkl):
+        lib = L.lib()
+        W_mu, W_rho, bias_mu, bias_rho = ctx.saved_tensors
+        pm, ps, conv = ctx.cfg
+        dev = W_mu.device
+        gkl = gkl.contiguous().float()
+        out = []
+        for mu, rho in ((W_mu, W_rho), (bias_mu, bias_rho)):
+            if mu is None:
+                out += [None, None]
+                continue
+            g_mu, g_rho = torch.zeros_like(mu), torch.zeros_like(rho)
+            rc = lib.bbb_kl_backward(_ptr(mu), _ptr(rho), C.c_uint64(mu.numel()), C.c_float(pm), C.c_float(ps),
+                                     C.c_int32(conv), _ptr(gkl), _ptr(g_mu), _ptr(g_rho), _stream(dev))
+            L.check(rc, "bbb_kl_backward")
+            out += [g_mu, g_rho]
+        return out[0], out[1], out[2], out[3], None, None, None
+
+
+# --------------------------------------------------------------------------- #
+# small direct wrappers
+# --------------------------------------------------------------------------- #
+def philox_normal(n: int, seed: int, stream_id: int, offset: int = 0, device="cuda") -> torch.Tensor:
+    """The engine's own noise stream, drawn on the host side of the boundary."""
+    out = torch.empty(n, dtype=torch.float32, device=device)
+    rc = L.lib().bbb_philox_normal_fill(_ptr(out), C.c_uint64(n), C.c_uint64(seed), C.c_uint64(stream_id),
+                                        C.c_uint64(offset), _stream(out.device))
+    L.check(rc, "bbb_philox_normal_fill")
+    return out
+
+
+def mc_combine(logits: torch.Tensor, want_moments: bool = False):
+    """logits [S,B,C] -> log_outputs [B,C] (main_bayesian.py:46-53) and optionally the
+    [3,B,C] sums (softmax, softmax^2, logits) for uncertainty_estimation.py:70-96."""
+    _require_cuda(logits, "mc_combine")
+    logits = logits.contiguous().float()
+    S, B, Cc = logits.shape
+    out = torch.empty(B, Cc, dtype=torch.float32, device=logits.device)
+    mom = torch.empty(3, B, Cc, dtype=torch.float32, device=logits.device) if want_moments else None
+    rc = L.lib().bbb_mc_combine(_ptr(logits), S, B, Cc, _ptr(out), _ptr(mom), _stream(logits.device))
+    L.check(rc, "bbb_mc_combine")
+    return (out, mom) if want_moments else out

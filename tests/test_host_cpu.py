@@ -1,0 +1,115 @@
+"""Host-side logic that runs without a GPU: the layer surface, state_dict keys,
+the C-ABI library loads and exports every declared symbol, errors are loud."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from tests.conftest import ROOT
+from tests.util import CFG_PRIORS
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as g
+    g.build()
+    return g.LIB
+
+
+def test_library_exports_every_declared_symbol(built):
+    hdr = open(os.path.join(ROOT, "include", "bbb_b200.h")).read()
+    hdr_nc = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(bbb_[a-z0-9_]+)\s*\(", hdr_nc))
+    assert len(declared) >= 12
+    lib = ctypes.CDLL(built)
+    for name in declared:
+        assert hasattr(lib, name), name
+    from pytorch_bayesiancnn_b200 import _lib
+    assert declared == set(_lib.SYMBOLS)
+    lib.bbb_abi_version.restype = ctypes.c_int32
+    assert lib.bbb_abi_version() == 1
+    assert ctypes.sizeof(_lib.LayerDesc) == 4 * 26 + 8
+
+
+def test_invalid_calls_return_error_codes_without_gpu(built):
+    from pytorch_bayesiancnn_b200 import _lib
+    lib = _lib.lib()
+    assert lib.bbb_kl_forward(None, None, 0, None, None, 0, 0.0, 0.1, 0, None, None, 0, None) == -1
+    assert b"NULL" in lib.bbb_last_error()
+    d = _lib.LayerDesc()
+    assert lib.bbb_conv2d_forward(ctypes.byref(d), None, None, None, None, None, None, None, None, None, None,
+                                  0, 0, None, 0, None) == -1
+    assert b"geometry" in lib.bbb_last_error()
+
+
+def test_layer_surface_and_state_dict_keys():
+    import layers
+    c = layers.BBB_Conv2d(3, 8, 5, stride=2, padding=1, bias=True, priors=None)
+    assert list(c.state_dict().keys()) == ["W_mu", "W_rho", "bias_mu", "bias_rho"]
+    assert c.kernel_size == (5, 5) and c.groups == 1 and c.use_bias and c.prior_sigma == 0.1
+    assert tuple(c.W_mu.shape) == (8, 3, 5, 5)
+    n = layers.BBB_LRT_Linear(7, 3, bias=False)
+    assert n.bias_mu is None and list(n.state_dict().keys()) == ["W_mu", "W_rho"]
+    r = layers.BBB_Conv2d(3, 4, (3, 5))
+    assert r.kernel_size == (3, 5)
+    # reset_parameters follows the priors (BBB/BBBConv.py:53-59)
+    big = layers.BBB_LRT_Linear(400, 300, priors=CFG_PRIORS)
+    assert abs(float(big.W_rho.mean()) + 5) < 0.01 and abs(float(big.W_mu.std()) - 0.1) < 0.01
+
+
+def test_module_wrapper_and_flatten():
+    import layers
+
+    class Net(layers.ModuleWrapper):
+        def __init__(self):
+            super().__init__()
+            self.flatten = layers.FlattenLayer(12)
+            self.id = torch.nn.Identity()
+
+    net = Net()
+    x = torch.arange(48.0).view(4, 3, 2, 2)
+    y, kl = net(x)
+    assert y.shape == (4, 12) and kl == 0.0
+    assert layers.FlattenLayer(24)(x).shape == (2, 24)       # no shape check, like the reference
+    net.set_flag("math", "bf16")
+    assert net.math == "bf16" and net.flatten.math == "bf16"
+
+
+def test_table_models_match_reference_structure():
+    from pytorch_bayesiancnn_b200.models import BBBAlexNet, BBBLeNet, BBB3Conv3FC, get_model
+    a = BBBAlexNet(10, 3, CFG_PRIORS, "lrt", "softplus")
+    assert [k for k, _ in a.named_children()] == ["conv1", "act1", "pool1", "conv2", "act2", "pool2", "conv3", "act3",
+                                                  "conv4", "act4", "conv5", "act5", "pool3", "flatten", "classifier"]
+    assert sum(p.numel() for p in a.parameters()) == 2 * 2175946
+    assert sum(p.numel() for p in BBBLeNet(10, 3, None, "bbb", "relu").parameters()) == 2 * 62006
+    assert sum(p.numel() for p in BBB3Conv3FC(10, 1, None).parameters()) == 2 * 1781034
+    assert a.num_classes == 10
+    with pytest.raises(ValueError):
+        BBBAlexNet(10, 3, None, "nope")
+    with pytest.raises(ValueError):
+        get_model("resnet", 3, 10, None, "lrt", "relu")
+
+
+def test_cpu_tensors_fail_loudly(built):
+    import layers
+    from pytorch_bayesiancnn_b200 import EngineError
+    lin = layers.BBB_Linear(4, 2)
+    if lin.W_mu.is_cuda:
+        pytest.skip("GPU present")
+    with pytest.raises(EngineError, match="no CPU fallback"):
+        lin(torch.randn(3, 4))
+    with pytest.raises(EngineError):
+        lin.kl_loss()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "pytorch_bayesiancnn_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert "oracle" not in src.replace("# checker", ""), f
+    for f in ("layers/__init__.py",):
+        assert "oracle" not in open(os.path.join(ROOT, f)).read()
