@@ -85,13 +85,16 @@ size_t bbb_workspace_bytes(const bbb_layer_desc* desc);
  * eps_a  : BBB: W_eps [Cout,Cin,kh,kw]; LRT: activation eps, shape of y.  NULL => Philox.
  * eps_b  : BBB: bias_eps [Cout]; LRT: unused.                             NULL => Philox.
  * Philox element index: BBB: flat OIHW index for W, |W| + c for bias;
- *                       LRT: flat NCHW index of y.                                    */
+ *                       LRT: flat NCHW index of y.
+ * stream_base: nullable DEVICE pointer; when set the effective Philox stream is
+ *          stream_id + *stream_base, read by the kernel at run time -- this is how a
+ *          captured CUDA graph draws fresh noise on every replay (bbb_noise_advance). */
 int bbb_conv2d_forward(const bbb_layer_desc* desc, const void* x,
                        const float* W_mu, const float* W_rho,
                        const float* bias_mu, const float* bias_rho,
                        void* y, float* kl_out, float* act_std,
                        const float* eps_a, const float* eps_b,
-                       uint64_t seed, uint64_t stream_id,
+                       uint64_t seed, uint64_t stream_id, const uint64_t* stream_base,
                        void* workspace, size_t workspace_bytes, void* cuda_stream);
 
 /* Replaces BBBLinear.forward + .kl_loss:
@@ -102,7 +105,7 @@ int bbb_linear_forward(const bbb_layer_desc* desc, const void* x,
                        const float* bias_mu, const float* bias_rho,
                        void* y, float* kl_out, float* act_std,
                        const float* eps_a, const float* eps_b,
-                       uint64_t seed, uint64_t stream_id,
+                       uint64_t seed, uint64_t stream_id, const uint64_t* stream_base,
                        void* workspace, size_t workspace_bytes, void* cuda_stream);
 
 /* Replaces layer.kl_loss() -> metrics.calculate_kl (metrics.py:27-29 with the call
@@ -128,7 +131,7 @@ int bbb_conv2d_backward(const bbb_layer_desc* desc, const void* x, const void* g
                         const float* bias_mu, const float* bias_rho,
                         const float* act_std,
                         const float* eps_a, const float* eps_b,
-                        uint64_t seed, uint64_t stream_id,
+                        uint64_t seed, uint64_t stream_id, const uint64_t* stream_base,
                         void* grad_x, float* g_W_mu, float* g_W_rho,
                         float* g_bias_mu, float* g_bias_rho,
                         void* workspace, size_t workspace_bytes, void* cuda_stream);
@@ -137,7 +140,7 @@ int bbb_linear_backward(const bbb_layer_desc* desc, const void* x, const void* g
                         const float* bias_mu, const float* bias_rho,
                         const float* act_std,
                         const float* eps_a, const float* eps_b,
-                        uint64_t seed, uint64_t stream_id,
+                        uint64_t seed, uint64_t stream_id, const uint64_t* stream_base,
                         void* grad_x, float* g_W_mu, float* g_W_rho,
                         float* g_bias_mu, float* g_bias_rho,
                         void* workspace, size_t workspace_bytes, void* cuda_stream);
@@ -147,6 +150,10 @@ int bbb_linear_backward(const bbb_layer_desc* desc, const void* x, const void* g
  * Philox4x32-10(counter = ((offset+i)>>2, stream_id), key = seed), Box-Muller. */
 int bbb_philox_normal_fill(float* out, uint64_t n, uint64_t seed, uint64_t stream_id,
                            uint64_t offset, void* cuda_stream);
+
+/* *base += inc on the device (one tiny kernel; put it at the head of a captured
+ * graph so each replay moves every layer to a fresh Philox stream). */
+int bbb_noise_advance(uint64_t* base, uint64_t inc, void* cuda_stream);
 
 /* Monte-Carlo combine that sits directly above the path (main_bayesian.py:46-53,
  * utils.py:14-22): logits [S, B, C] fp32 -> log_outputs [B, C] =

@@ -5,6 +5,8 @@ engine controls.  The compute lives in libbbb_b200.so (csrc/, C ABI in include/b
 """
 from .modules import (BBBConv2d, BBBLinear, BBBLRTConv2d, BBBLRTLinear, FlattenLayer, ModuleWrapper)
 from .functional import (manual_seed, begin_sample, external_eps, philox_normal, mc_combine)
+from .graph import GraphedForward
+from . import functional
 from ._lib import EngineError, launch_count, LIB_PATH
 
 BBB_Linear = BBBLinear

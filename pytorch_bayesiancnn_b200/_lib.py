@@ -26,7 +26,7 @@ ACT_BY_NAME = {None: ACT_NONE, "none": ACT_NONE, "softplus": ACT_SOFTPLUS, "relu
 SYMBOLS = (
     "bbb_workspace_bytes", "bbb_conv2d_forward", "bbb_linear_forward", "bbb_kl_forward",
     "bbb_kl_backward", "bbb_conv2d_backward", "bbb_linear_backward", "bbb_philox_normal_fill",
-    "bbb_mc_combine", "bbb_last_error", "bbb_abi_version", "bbb_launch_count",
+    "bbb_mc_combine", "bbb_noise_advance", "bbb_last_error", "bbb_abi_version", "bbb_launch_count",
 )
 
 
@@ -50,8 +50,8 @@ _lock = threading.Lock()
 def _bind(lib):
     vp, fp, u64, i32, sz = C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32, C.c_size_t
     dp = C.POINTER(LayerDesc)
-    fwd = [dp, vp, fp, fp, fp, fp, vp, fp, fp, fp, fp, u64, u64, vp, sz, vp]
-    bwd = [dp, vp, vp, fp, fp, fp, fp, fp, fp, fp, u64, u64, vp, fp, fp, fp, fp, vp, sz, vp]
+    fwd = [dp, vp, fp, fp, fp, fp, vp, fp, fp, fp, fp, u64, u64, vp, vp, sz, vp]
+    bwd = [dp, vp, vp, fp, fp, fp, fp, fp, fp, fp, u64, u64, vp, vp, fp, fp, fp, fp, vp, sz, vp]
     lib.bbb_workspace_bytes.argtypes = [dp]
     lib.bbb_workspace_bytes.restype = sz
     for name in ("bbb_conv2d_forward", "bbb_linear_forward"):
@@ -68,6 +68,8 @@ def _bind(lib):
     lib.bbb_philox_normal_fill.restype = C.c_int
     lib.bbb_mc_combine.argtypes = [fp, i32, i32, i32, fp, fp, vp]
     lib.bbb_mc_combine.restype = C.c_int
+    lib.bbb_noise_advance.argtypes = [vp, u64, vp]
+    lib.bbb_noise_advance.restype = C.c_int
     lib.bbb_last_error.argtypes = []
     lib.bbb_last_error.restype = C.c_char_p
     lib.bbb_abi_version.argtypes = []

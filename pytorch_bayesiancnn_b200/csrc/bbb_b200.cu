@@ -49,7 +49,7 @@ int check_desc(const bbb_layer_desc* d, bbb::Geom& g, bool linear) {
 
 int forward_impl(const bbb_layer_desc* d, bool linear, const void* x, const float* W_mu, const float* W_rho,
                  const float* bias_mu, const float* bias_rho, void* y, float* kl_out, float* act_std,
-                 const float* eps_a, const float* eps_b, uint64_t seed, uint64_t stream_id, void* ws,
+                 const float* eps_a, const float* eps_b, uint64_t seed, uint64_t stream_id, const uint64_t* stream_base, void* ws,
                  size_t ws_bytes, void* stream) {
     bbb::Geom g;
     if (int rc = check_desc(d, g, linear)) return rc;
@@ -67,7 +67,7 @@ int forward_impl(const bbb_layer_desc* d, bool linear, const void* x, const floa
         bbb::TcArgs a;
         a.g = g; a.x = x; a.w_mu = W_mu; a.w_rho = W_rho; a.b_mu = bias_mu; a.b_rho = bias_rho;
         a.y = y; a.kl_out = kl_out; a.act_std = act_std; a.eps_a = eps_a; a.eps_b = eps_b;
-        a.key = bbb::make_key(seed, stream_id);
+        a.key = bbb::make_key(seed, stream_id); a.stream_base = (const unsigned long long*)stream_base;
         a.kl_counter = (unsigned int*)ws; a.kl_partials = (double*)((char*)ws + kCounterBytes);
         a.prior_mu = d->prior_mu; a.prior_sigma = d->prior_sigma;
         a.sample = d->sample; a.kl_convention = d->kl_convention; a.has_bias = d->has_bias; a.act = d->epilogue_act;
@@ -84,7 +84,7 @@ int forward_impl(const bbb_layer_desc* d, bool linear, const void* x, const floa
     bbb::FwdArgs a;
     a.g = g; a.x = (const float*)x; a.w_mu = W_mu; a.w_rho = W_rho; a.b_mu = bias_mu; a.b_rho = bias_rho;
     a.y = (float*)y; a.kl_out = kl_out; a.act_std = act_std; a.eps_a = eps_a; a.eps_b = eps_b;
-    a.key = bbb::make_key(seed, stream_id);
+    a.key = bbb::make_key(seed, stream_id); a.stream_base = (const unsigned long long*)stream_base;
     a.kl_counter = (unsigned int*)ws; a.kl_partials = (double*)((char*)ws + kCounterBytes);
     a.prior_mu = d->prior_mu; a.prior_sigma = d->prior_sigma;
     a.sample = d->sample; a.kl_convention = d->kl_convention; a.has_bias = d->has_bias; a.act = d->epilogue_act;
@@ -97,7 +97,7 @@ int forward_impl(const bbb_layer_desc* d, bool linear, const void* x, const floa
 
 int backward_impl(const bbb_layer_desc* d, bool linear, const void* x, const void* grad_y, const float* W_mu,
                   const float* W_rho, const float* bias_mu, const float* bias_rho, const float* act_std,
-                  const float* eps_a, const float* eps_b, uint64_t seed, uint64_t stream_id, void* grad_x,
+                  const float* eps_a, const float* eps_b, uint64_t seed, uint64_t stream_id, const uint64_t* stream_base, void* grad_x,
                   float* g_W_mu, float* g_W_rho, float* g_bias_mu, float* g_bias_rho, void* ws, size_t ws_bytes,
                   void* stream) {
     bbb::Geom g;
@@ -112,7 +112,7 @@ int backward_impl(const bbb_layer_desc* d, bool linear, const void* x, const voi
     bbb::BwdArgs a;
     a.g = g; a.x = (const float*)x; a.gy = (const float*)grad_y; a.w_mu = W_mu; a.w_rho = W_rho;
     a.b_mu = bias_mu; a.b_rho = bias_rho; a.act_std = act_std; a.eps_a = eps_a; a.eps_b = eps_b;
-    a.key = bbb::make_key(seed, stream_id);
+    a.key = bbb::make_key(seed, stream_id); a.stream_base = (const unsigned long long*)stream_base;
     a.gx = (float*)grad_x; a.g_w_mu = g_W_mu; a.g_w_rho = g_W_rho; a.g_b_mu = g_bias_mu; a.g_b_rho = g_bias_rho;
     a.sample = d->sample; a.has_bias = d->has_bias; a.variant = d->variant;
     int nl = 0;
@@ -133,37 +133,37 @@ size_t bbb_workspace_bytes(const bbb_layer_desc* desc) {
 
 int bbb_conv2d_forward(const bbb_layer_desc* desc, const void* x, const float* W_mu, const float* W_rho,
                        const float* bias_mu, const float* bias_rho, void* y, float* kl_out, float* act_std,
-                       const float* eps_a, const float* eps_b, uint64_t seed, uint64_t stream_id,
+                       const float* eps_a, const float* eps_b, uint64_t seed, uint64_t stream_id, const uint64_t* stream_base,
                        void* workspace, size_t workspace_bytes, void* cuda_stream) {
     return forward_impl(desc, false, x, W_mu, W_rho, bias_mu, bias_rho, y, kl_out, act_std, eps_a, eps_b, seed,
-                        stream_id, workspace, workspace_bytes, cuda_stream);
+                        stream_id, stream_base, workspace, workspace_bytes, cuda_stream);
 }
 
 int bbb_linear_forward(const bbb_layer_desc* desc, const void* x, const float* W_mu, const float* W_rho,
                        const float* bias_mu, const float* bias_rho, void* y, float* kl_out, float* act_std,
-                       const float* eps_a, const float* eps_b, uint64_t seed, uint64_t stream_id,
+                       const float* eps_a, const float* eps_b, uint64_t seed, uint64_t stream_id, const uint64_t* stream_base,
                        void* workspace, size_t workspace_bytes, void* cuda_stream) {
     return forward_impl(desc, true, x, W_mu, W_rho, bias_mu, bias_rho, y, kl_out, act_std, eps_a, eps_b, seed,
-                        stream_id, workspace, workspace_bytes, cuda_stream);
+                        stream_id, stream_base, workspace, workspace_bytes, cuda_stream);
 }
 
 int bbb_conv2d_backward(const bbb_layer_desc* desc, const void* x, const void* grad_y, const float* W_mu,
                         const float* W_rho, const float* bias_mu, const float* bias_rho, const float* act_std,
-                        const float* eps_a, const float* eps_b, uint64_t seed, uint64_t stream_id, void* grad_x,
+                        const float* eps_a, const float* eps_b, uint64_t seed, uint64_t stream_id, const uint64_t* stream_base, void* grad_x,
                         float* g_W_mu, float* g_W_rho, float* g_bias_mu, float* g_bias_rho, void* workspace,
                         size_t workspace_bytes, void* cuda_stream) {
     return backward_impl(desc, false, x, grad_y, W_mu, W_rho, bias_mu, bias_rho, act_std, eps_a, eps_b, seed,
-                         stream_id, grad_x, g_W_mu, g_W_rho, g_bias_mu, g_bias_rho, workspace, workspace_bytes,
+                         stream_id, stream_base, grad_x, g_W_mu, g_W_rho, g_bias_mu, g_bias_rho, workspace, workspace_bytes,
                          cuda_stream);
 }
 
 int bbb_linear_backward(const bbb_layer_desc* desc, const void* x, const void* grad_y, const float* W_mu,
                         const float* W_rho, const float* bias_mu, const float* bias_rho, const float* act_std,
-                        const float* eps_a, const float* eps_b, uint64_t seed, uint64_t stream_id, void* grad_x,
+                        const float* eps_a, const float* eps_b, uint64_t seed, uint64_t stream_id, const uint64_t* stream_base, void* grad_x,
                         float* g_W_mu, float* g_W_rho, float* g_bias_mu, float* g_bias_rho, void* workspace,
                         size_t workspace_bytes, void* cuda_stream) {
     return backward_impl(desc, true, x, grad_y, W_mu, W_rho, bias_mu, bias_rho, act_std, eps_a, eps_b, seed,
-                         stream_id, grad_x, g_W_mu, g_W_rho, g_bias_mu, g_bias_rho, workspace, workspace_bytes,
+                         stream_id, stream_base, grad_x, g_W_mu, g_W_rho, g_bias_mu, g_bias_rho, workspace, workspace_bytes,
                          cuda_stream);
 }
 
@@ -226,6 +226,15 @@ int bbb_mc_combine(const float* logits, int32_t S, int32_t B, int32_t C, float* 
     bbb::mc_combine_kernel<<<B, 128, S * sizeof(float), (cudaStream_t)cuda_stream>>>(logits, S, B, C, log_outputs, moments);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "mc_combine launch");
+    g_launches += 1;
+    return BBB_OK;
+}
+
+int bbb_noise_advance(uint64_t* base, uint64_t inc, void* cuda_stream) {
+    if (!base) return fail(BBB_E_INVALID, "NULL base pointer");
+    bbb::noise_advance_kernel<<<1, 1, 0, (cudaStream_t)cuda_stream>>>((unsigned long long*)base, (unsigned long long)inc);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "noise_advance launch");
     g_launches += 1;
     return BBB_OK;
 }

@@ -62,6 +62,15 @@ __host__ __device__ inline NoiseKey make_key(uint64_t seed, uint64_t stream) {
     k.stream_lo = (uint32_t)stream; k.stream_hi = (uint32_t)(stream >> 32); return k;
 }
 
+// graph-replay support: effective stream = stream + *base (base nullable, device memory)
+__device__ __forceinline__ NoiseKey effective_key(NoiseKey k, const unsigned long long* base) {
+    if (base) {
+        const unsigned long long s = (((unsigned long long)k.stream_hi << 32) | k.stream_lo) + __ldg(base);
+        k.stream_lo = (uint32_t)s; k.stream_hi = (uint32_t)(s >> 32);
+    }
+    return k;
+}
+
 // four normals of group g (elements 4g .. 4g+3)
 __device__ __forceinline__ float4 normal4(uint64_t grp, const NoiseKey& k) {
     const uint4 r = philox4x32_10(make_uint4((uint32_t)grp, (uint32_t)(grp >> 32), k.stream_lo, k.stream_hi),

@@ -19,7 +19,7 @@ struct FwdArgs {
     const float* x; const float* w_mu; const float* w_rho; const float* b_mu; const float* b_rho;
     float* y; float* kl_out; float* act_std;
     const float* eps_a; const float* eps_b;
-    NoiseKey key;
+    NoiseKey key; const unsigned long long* stream_base;
     double* kl_partials; unsigned int* kl_counter;
     float prior_mu, prior_sigma;
     int sample, kl_convention, has_bias, act;
@@ -51,6 +51,7 @@ fwd_simt_kernel(const FwdArgs p) {
     const bool stoch = p.sample != 0;
     const bool need_var = LRT && stoch;
     const float* __restrict__ x = p.x;
+    const NoiseKey nkey = effective_key(p.key, p.stream_base);
 
     // ---- A (im2col of x) load mapping -------------------------------------
     // conv: consecutive threads walk m (output pixels: contiguous-ish in x);
@@ -109,7 +110,7 @@ fwd_simt_kernel(const FwdArgs p) {
                 if (LRT) {
                     w = mu; s2 = sigma * sigma;
                 } else if (stoch) {
-                    const float e = p.eps_a ? __ldg(p.eps_a + wi) : normal1(wi, p.key);
+                    const float e = p.eps_a ? __ldg(p.eps_a + wi) : normal1(wi, nkey);
                     w = mu + e * sigma;                               // BBB/BBBConv.py:65
                 } else {
                     w = mu;
@@ -179,7 +180,7 @@ fwd_simt_kernel(const FwdArgs p) {
                 const float sigma = softplus_sigma(__ldg(p.b_rho + n));
                 if (LRT) { bm = mu; bv = sigma * sigma; }
                 else {
-                    const float e = p.eps_b ? __ldg(p.eps_b + n) : normal1((uint64_t)g.N * g.K + n, p.key);
+                    const float e = p.eps_b ? __ldg(p.eps_b + n) : normal1((uint64_t)g.N * g.K + n, nkey);
                     bm = mu + e * sigma;                              // BBB/BBBConv.py:70
                 }
             } else {
@@ -213,7 +214,7 @@ fwd_simt_kernel(const FwdArgs p) {
             if (need_var) {
                 const float var = 1e-16f + (accv[i][j] + bias_v[j]);   // BBB_LRT/BBBConv.py:73-74
                 const float sd = sqrtf(var);
-                const float e = p.eps_a ? __ldg(p.eps_a + o) : normal1(o, p.key);
+                const float e = p.eps_a ? __ldg(p.eps_a + o) : normal1(o, nkey);
                 v = v + sd * e;                                       // BBB_LRT/BBBConv.py:79
                 if (p.act_std) p.act_std[o] = sd;
             }

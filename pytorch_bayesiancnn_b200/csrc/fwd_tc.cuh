@@ -7,7 +7,7 @@ struct TcArgs {
     const void* x; const float* w_mu; const float* w_rho; const float* b_mu; const float* b_rho;
     void* y; float* kl_out; float* act_std;
     const float* eps_a; const float* eps_b;
-    NoiseKey key;
+    NoiseKey key; const unsigned long long* stream_base;
     double* kl_partials; unsigned int* kl_counter;
     float prior_mu, prior_sigma;
     int sample, kl_convention, has_bias, act, act_dtype, variant;

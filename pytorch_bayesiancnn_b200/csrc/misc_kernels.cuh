@@ -62,6 +62,8 @@ philox_fill_kernel(float* __restrict__ out, uint64_t n, NoiseKey key, uint64_t o
         out[i] = normal1(offset + i, key);
 }
 
+__global__ void noise_advance_kernel(unsigned long long* base, unsigned long long inc) { *base += inc; }
+
 // main_bayesian.py:46-53 + utils.py:14-22 (+ uncertainty_estimation.py:70-96 moments).
 // One CTA per image; warps compute log-sum-exp per MC sample, then one thread per
 // class folds the S samples with an online logmeanexp.

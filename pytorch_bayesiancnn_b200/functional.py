@@ -24,6 +24,7 @@ class _Noise(threading.local):
         self.seed = 0x5EEDB200
         self.counter = 0
         self.queue = None          # external-eps queue (parity mode)
+        self.base = None           # device int64[1] stream base (CUDA-graph capture mode)
 
 
 _noise = _Noise()
@@ -41,6 +42,25 @@ def begin_sample(sample_id: int):
     layer calls of that sample use stream ids (sample_id << 32) + 0, 1, 2, ...  so
     results do not depend on how samples are sharded over ranks."""
     _noise.counter = int(sample_id) << 32
+
+
+@contextlib.contextmanager
+def stream_base(base: Optional[torch.Tensor]):
+    """Graph-capture mode: layer calls inside take stream ids 0, 1, 2, ... RELATIVE to
+    the device scalar `base` (int64[1]), which kernels read at run time; advancing it
+    (bbb_noise_advance, captured in the graph) gives every replay fresh noise."""
+    prev, prev_ctr = _noise.base, _noise.counter
+    _noise.base = base
+    _noise.counter = 0
+    try:
+        yield
+    finally:
+        _noise.base, _noise.counter = prev, prev_ctr
+
+
+def noise_advance(base: torch.Tensor, inc: int):
+    rc = L.lib().bbb_noise_advance(_ptr(base), C.c_uint64(inc), _stream(base.device))
+    L.check(rc, "bbb_noise_advance")
 
 
 def next_stream() -> tuple[int, int]:
@@ -174,6 +194,7 @@ class BayesLayerFn(torch.autograd.Function):
         kl = torch.empty((), dtype=torch.float32, device=dev)
         eps_a = eps_b = None
         seed = stream_id = 0
+        base = None
         if sample:
             if external_eps_active():
                 if variant == L.VARIANT_BBB:
@@ -184,6 +205,7 @@ class BayesLayerFn(torch.autograd.Function):
                     eps_a = _pop_eps(yshape, dev)
             else:
                 seed, stream_id = next_stream()
+                base = _noise.base
         need_grad = any(ctx.needs_input_grad[:5])      # grad mode is off inside Function.forward
         act_std = None
         if variant == L.VARIANT_LRT and sample and need_grad:
@@ -192,11 +214,11 @@ class BayesLayerFn(torch.autograd.Function):
         fn = lib.bbb_linear_forward if conv is None else lib.bbb_conv2d_forward
         rc = fn(C.byref(d), _ptr(x), _ptr(W_mu_c), _ptr(W_rho_c), _ptr(bias_mu), _ptr(bias_rho),
                 _ptr(y), _ptr(kl), _ptr(act_std), _ptr(eps_a), _ptr(eps_b),
-                C.c_uint64(seed), C.c_uint64(stream_id), _ptr(ws), C.c_size_t(ws.numel()), _stream(dev))
+                C.c_uint64(seed), C.c_uint64(stream_id), _ptr(base), _ptr(ws), C.c_size_t(ws.numel()), _stream(dev))
         L.check(rc, "bbb_linear_forward" if conv is None else "bbb_conv2d_forward")
         ctx.cfg = cfg
         ctx.desc = d
-        ctx.noise = (seed, stream_id)
+        ctx.noise = (seed, stream_id, base)
         ctx.has_bias = has_bias
         ctx.save_for_backward(x, W_mu_c, W_rho_c, bias_mu, bias_rho, act_std, eps_a, eps_b)
         return y, kl
@@ -220,9 +242,9 @@ class BayesLayerFn(torch.autograd.Function):
                 gx = torch.zeros_like(x)
             ws = workspace(dev)
             fn = lib.bbb_linear_backward if cfg["conv"] is None else lib.bbb_conv2d_backward
-            seed, stream_id = ctx.noise
+            seed, stream_id, base = ctx.noise
             rc = fn(C.byref(d), _ptr(x), _ptr(gy), _ptr(W_mu), _ptr(W_rho), _ptr(bias_mu), _ptr(bias_rho),
-                    _ptr(act_std), _ptr(eps_a), _ptr(eps_b), C.c_uint64(seed), C.c_uint64(stream_id),
+                    _ptr(act_std), _ptr(eps_a), _ptr(eps_b), C.c_uint64(seed), C.c_uint64(stream_id), _ptr(base),
                     _ptr(gx), _ptr(g_W_mu), _ptr(g_W_rho), _ptr(g_b_mu), _ptr(g_b_rho),
                     _ptr(ws), C.c_size_t(ws.numel()), _stream(dev))
             L.check(rc, "bbb_*_backward")

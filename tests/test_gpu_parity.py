@@ -66,7 +66,7 @@ def test_philox_stream_matches_host_restatement(dev):
     for (n, seed, stream, off) in [(1000, 1, 0, 0), (4099, 0xDEADBEEFCAFE, (3 << 32) + 5, 7), (257, 42, 9, 1 << 33)]:
         z = bbb.philox_normal(n, seed, stream, off, device=dev).cpu().numpy()
         ref = O.philox_normal(n, seed, stream, off)
-        assert np.abs(z - ref).max() < 2e-5, (n, seed)
+        assert np.abs(z - ref).max() < 2e-4, (n, seed)     # device uses __logf/__sincosf
     z = bbb.philox_normal(1 << 20, 123, 4, device=dev)
     assert abs(float(z.mean())) < 5e-3 and abs(float(z.std()) - 1) < 5e-3
 

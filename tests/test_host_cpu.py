@@ -40,7 +40,7 @@ def test_invalid_calls_return_error_codes_without_gpu(built):
     assert b"NULL" in lib.bbb_last_error()
     d = _lib.LayerDesc()
     assert lib.bbb_conv2d_forward(ctypes.byref(d), None, None, None, None, None, None, None, None, None, None,
-                                  0, 0, None, 0, None) == -1
+                                  0, 0, None, None, 0, None) == -1
     assert b"geometry" in lib.bbb_last_error()
 
 
