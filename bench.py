@@ -1,0 +1,438 @@
+#!/usr/bin/env python
+"""bench.py -- BBBAlexNet forward + KL images/sec on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one synthetic batch: BBBAlexNet
+(CIFAR-10 shape, 3x32x32, batch 512), ONE Monte-Carlo weight sample per GPU,
+all six Bayesian layers + the model file's own activation/pool/flatten modules +
+the summed KL scalar.  With N GPUs the num_ens MC loop (main_bayesian.py:46-49)
+is the shard axis: rank r runs sample r of the SAME batch and one NCCL all-reduce
+combines sum_j softmax_j and the KL -> weak scaling, value =
+B * N * K / t.
+
+Printed JSON (rank 0, one line): the driver contract + `roofline`, `cpu_baseline`,
+`e2e`, `clocks`, `gpu_launches`, `per_layer`.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+PRIORS = {"prior_mu": 0, "prior_sigma": 0.1, "posterior_mu_initial": (0, 0.1),
+          "posterior_rho_initial": (-5, 0.1)}          # config_bayesian.py:4-9
+METRIC = "BBBAlexNet fwd+KL images/sec"
+L2_FLUSH_BYTES = 256 << 20
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# --------------------------------------------------------------------------- #
+# clocks
+# --------------------------------------------------------------------------- #
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- #
+# workload
+# --------------------------------------------------------------------------- #
+def layer_table(batch, classes=10):
+    """Algorithmic FLOPs / bytes per Bayesian layer."""
+    spec = [("conv1", 3, 32, 64, 11, 4, 5), ("conv2", 64, 4, 192, 5, 1, 2), ("conv3", 192, 2, 384, 3, 1, 1),
+            ("conv4", 384, 2, 256, 3, 1, 1), ("conv5", 256, 2, 128, 3, 1, 1), ("classifier", 128, 1, classes, 1, 1, 0)]
+    rows = []
+    for name, cin, hin, cout, k, s, p in spec:
+        ho = (hin + 2 * p - k) // s + 1
+        K = cin * k * k
+        rows.append({"name": name, "M": batch * ho * ho, "N": cout, "K": K,
+                     "flops_mean": 2.0 * batch * ho * ho * cout * K,
+                     "x_elems": batch * cin * hin * hin, "y_elems": batch * cout * ho * ho,
+                     "params": cout * K + cout})
+    return rows
+
+
+def algorithmic(row, variant, act_bytes=4):
+    v = 2.0 if variant == "lrt" else 1.0
+    flops = row["flops_mean"] * v
+    byts = row["x_elems"] * act_bytes + 2 * row["params"] * 4 + row["y_elems"] * act_bytes + 4
+    return flops, byts
+
+
+def build_net(variant, classes, device, math):
+    import pytorch_bayesiancnn_b200 as bbb  # noqa: F401
+    from pytorch_bayesiancnn_b200.models import BBBAlexNet
+    torch.manual_seed(123)
+    net = BBBAlexNet(classes, 3, PRIORS, variant, "softplus")
+    with torch.no_grad():                       # identical params on every rank, drawn on the CPU generator
+        g = torch.Generator().manual_seed(123)
+        for name, p in net.named_parameters():
+            mean = -5.0 if name.endswith("rho") else 0.0
+            p.copy_(torch.empty(p.shape).normal_(mean, 0.1, generator=g))
+    net = net.to(device).train()
+    net.set_flag("math", math)
+    return net
+
+
+# --------------------------------------------------------------------------- #
+# our arm
+# --------------------------------------------------------------------------- #
+def run_ours(args):
+    import pytorch_bayesiancnn_b200 as bbb
+    from pytorch_bayesiancnn_b200 import functional as Fn
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run for --gpus > 1")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=dev)
+    B, C = args.batch, args.classes
+    pk = peaks()
+
+    net = build_net(args.variant, C, dev, args.math)
+    gx = torch.Generator().manual_seed(0)
+    n_inputs = 4
+    x_host = [torch.randn(B, 3, 32, 32, generator=gx).pin_memory() for _ in range(n_inputs)]
+    x_dev = [t.to(dev) for t in x_host]
+    bbb.manual_seed(2024)
+    # rank r owns MC sample r: its Philox streams start at r << 32 (functional.begin_sample)
+    graphed = bbb.GraphedForward(net, x_dev[0], first_stream=rank << 32)
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    comb = torch.zeros(B * C + 1, dtype=torch.float32, device=dev)
+
+    def step(i, xin=None):
+        logits, kl = graphed(xin)
+        if dist is not None:
+            comb[:B * C] = torch.softmax(logits, 1).reshape(-1)
+            comb[B * C] = kl
+            dist.all_reduce(comb)               # ONE collective: sum_j softmax_j and sum KL
+            return torch.log(comb[:B * C] / world).view(B, C), comb[B * C] / world
+        return logits, kl
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    # ---- device-resident throughput: per-step events, L2 flushed (untimed) between steps ----
+    for i in range(args.warmup):
+        step(i, x_dev[i % n_inputs])
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = bbb.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()                            # evict L2 (126 MB) -- not timed
+        graphed.x.copy_(x_dev[i % n_inputs])     # stage the step's input (device-resident) -- not timed
+        ev[i][0].record()
+        step(i)
+        ev[i][1].record()
+    sync_all()
+    wall = time.perf_counter() - wall0
+    launches = bbb.launch_count() - l0
+    per_step = [a.elapsed_time(b) for a, b in ev]
+    t_ms = torch.tensor([sum(per_step)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(t_ms.item())
+    value = B * world * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the public API: pinned host input -> H2D -> forward -> D2H ----
+    out_host = torch.empty(B, C, dtype=torch.float32).pin_memory()
+    kl_host = torch.empty(1, dtype=torch.float32).pin_memory()
+    copy_stream = torch.cuda.Stream(device=dev)
+    staging = [torch.empty_like(x_dev[0]) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    main = torch.cuda.current_stream(dev)
+
+    def e2e_run(nsteps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        e0.record(main)
+        copy_stream.wait_event(e0)
+        with torch.cuda.stream(copy_stream):
+            staging[0].copy_(x_host[0], non_blocking=True)
+            ready[0].record(copy_stream)
+        for i in range(nsteps):
+            s = i & 1
+            if i + 1 < nsteps:                  # prefetch the next batch while this one computes
+                with torch.cuda.stream(copy_stream):
+                    if i >= 1:
+                        copy_stream.wait_event(consumed[s ^ 1])
+                    staging[s ^ 1].copy_(x_host[(i + 1) % n_inputs], non_blocking=True)
+                    ready[s ^ 1].record(copy_stream)
+            main.wait_event(ready[s])
+            lo, kl = step(i, staging[s])
+            consumed[s].record(main)
+            out_host.copy_(lo, non_blocking=True)
+            kl_host.copy_(kl.reshape(1), non_blocking=True)
+        e1.record(main)
+        sync_all()
+        return e0.elapsed_time(e1)
+
+    e2e_run(max(3, args.warmup))
+    e_ms = torch.tensor([e2e_run(args.steps)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = B * world * args.steps / (float(e_ms.item()) * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- per-layer kernel timing + roofline of the dominant kernel (rank 0) ----
+    per_layer, roof = [], None
+    if rank == 0:
+        per_layer, roof = layer_rooflines(net, x_dev[0], args, pk, flush)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference(args, seconds=args.cpu_seconds)
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.math == "fp32" else "bf16 operands, f32 accumulate",
+            "data": "synthetic (randn inputs, random-init params N(0,0.1)/rho N(-5,0.1))",
+            "config": {"workload": f"BBBAlexNet-{C} CIFAR-10 shape 3x32x32, batch {B}, {args.variant} layers, "
+                                   f"softplus, 1 MC sample per GPU per step (MC samples sharded over GPUs)",
+                       "batch": B, "variant": args.variant, "math": args.math, "mc_samples_total": world,
+                       "parallelism": f"mc{world}", "l2": "flushed between timed steps (256 MiB memset, untimed)",
+                       "launch": "CUDA graph replay of the full forward (layer kernels + aten act/pool)"},
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * 3 * 32 * 32 * 4,
+                    "d2h_bytes_per_step": B * C * 4 + 4},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof,
+            "per_layer": per_layer,
+            "cpu_baseline": cpu,
+            "wall_s_timed_loop": wall,
+        }
+        print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def layer_rooflines(net, x, args, pk, flush, reps=20):
+    """Time each Bayesian layer's fused kernel alone (CUDA events on the launching
+    stream, L2 flushed between launches) and report algorithmic FLOP/s and B/s."""
+    import pytorch_bayesiancnn_b200 as bbb
+    rows = layer_table(args.batch, args.classes)
+    acts = {}
+    h = x
+    with torch.no_grad():
+        for name, m in net.named_children():
+            if hasattr(m, "W_mu"):
+                acts[name] = h
+            h = m(h)
+    out = []
+    for row in rows:
+        m = getattr(net, row["name"])
+        xin = acts[row["name"]].contiguous()
+        times = []
+        with torch.no_grad():
+            for _ in range(3):
+                m(xin)
+            for _ in range(reps):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); m(xin); e1.record()
+                torch.cuda.synchronize()
+                times.append(e0.elapsed_time(e1))
+        ms = statistics.median(times)
+        fl, by = algorithmic(row, args.variant)
+        t_tc = fl / (pk["tf_burst"] * 1e12)
+        t_hbm = by / (pk["hbm_gbs"] * 1e9)
+        bound = "tensor" if t_tc >= t_hbm else "hbm"
+        out.append({"name": row["name"], "gemm": [row["M"], row["N"], row["K"]], "ms": ms,
+                    "gflop": fl / 1e9, "mbytes": by / 1e6, "bound": bound,
+                    "tflops": fl / (ms * 1e-3) / 1e12, "gbs": by / (ms * 1e-3) / 1e9,
+                    "frac": max(t_tc, t_hbm) / (ms * 1e-3)})
+    top = max(out, key=lambda r: r["ms"])
+    if top["bound"] == "tensor":
+        roof = {"kernel": top["name"], "bound": "tensor", "achieved": top["tflops"], "peak": pk["tf_burst"],
+                "unit": "TFLOP/s", "frac": top["tflops"] / pk["tf_burst"], "traffic": None,
+                "peak_source": pk["source"] + ", burst bf16 (kernel timed alone)"}
+    else:
+        roof = {"kernel": top["name"], "bound": "hbm", "achieved": top["gbs"], "peak": pk["hbm_gbs"],
+                "unit": "GB/s", "frac": top["gbs"] / pk["hbm_gbs"], "traffic": None,
+                "peak_source": pk["source"]}
+    t_roof = sum(max(algorithmic(r, args.variant)[0] / (pk["tf_burst"] * 1e12),
+                     algorithmic(r, args.variant)[1] / (pk["hbm_gbs"] * 1e9)) for r in rows)
+    roof["net_t_roof_us"] = t_roof * 1e6
+    roof["net_layer_kernels_us"] = sum(r["ms"] for r in out) * 1e3
+    return out, roof
+
+
+# --------------------------------------------------------------------------- #
+# CPU reference arm (the oracle port of the reference's CPU path)
+# --------------------------------------------------------------------------- #
+def cpu_step_fn(args):
+    from oracle import bbb_oracle as O               # bench's cpu_baseline leg may use the oracle
+    torch.set_num_threads(os.cpu_count() or 1)
+    params = O.init_params("alexnet", args.classes, 3, PRIORS, seed=123)
+    x = torch.randn(args.batch, 3, 32, 32, generator=torch.Generator().manual_seed(0))
+    shapes = O.eps_shapes("alexnet", args.classes, 3, args.variant, args.batch)
+
+    def one():
+        with torch.no_grad():
+            # the reference draws eps on the CPU generator inside every forward (BBB/BBBConv.py:63)
+            eps = [torch.empty(s).normal_(0, 1) for s in shapes]
+            logits, kl = O.net_forward("alexnet", params, x, eps, args.variant, "softplus", 0.0, 0.1, args.classes)
+            return float(kl) + float(logits[0, 0])
+    return one
+
+
+def cpu_reference(args, seconds=10.0):
+    one = cpu_step_fn(args)
+    for _ in range(2):
+        one()
+    ts = []
+    t_end = time.perf_counter() + seconds
+    while time.perf_counter() < t_end or len(ts) < 5:
+        t0 = time.perf_counter(); one(); ts.append(time.perf_counter() - t0)
+        if len(ts) >= 200:
+            break
+    med = statistics.median(ts)
+    return {"value": args.batch / med, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{len(ts)} forwards of the full batch-{args.batch} workload (median {med * 1e3:.1f} ms, "
+                      f"min {min(ts) * 1e3:.1f} ms), torch-CPU restatement of the reference incl. its CPU eps draws",
+            "cpu_model": cpu_model()}
+
+
+def cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    one = cpu_step_fn(args)
+    steps = min(args.steps, 200)
+    for _ in range(args.warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = time.perf_counter() - t0
+    val = args.batch * steps / dt
+    cores = torch.get_num_threads()
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus,
+           "steps": steps, "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"BBBAlexNet-{args.classes} CIFAR-10 shape 3x32x32, batch {args.batch}, "
+                                  f"{args.variant} layers, softplus, 1 MC sample per step", "batch": args.batch,
+                      "variant": args.variant},
+           "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port",
+                            "sample": f"{steps} forwards of the full batch-{args.batch} workload",
+                            "cpu_model": cpu_model()},
+           "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--variant", default="lrt", choices=["lrt", "bbb"])
+    ap.add_argument("--math", default=os.environ.get("BBB_B200_MATH", "fp32"), choices=["fp32", "bf16", "auto"])
+    ap.add_argument("--batch", type=int, default=512)
+    ap.add_argument("--classes", type=int, default=10)
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device (the engine has no CPU fallback); use --impl reference for the CPU arm")
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
