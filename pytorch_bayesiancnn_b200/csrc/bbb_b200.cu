@@ -26,6 +26,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 constexpr size_t kCounterBytes = 64;
 constexpr size_t kMaxKlSlots = 4096;
 constexpr size_t kBaseWorkspace = kCounterBytes + kMaxKlSlots * sizeof(double);
+constexpr size_t kTcOffset = (kBaseWorkspace + 1023) / 1024 * 1024;   // prepared-operand region (tcgen05 path)
 
 int sm_count() {
     static int n = 0;
@@ -64,7 +65,12 @@ int forward_impl(const bbb_layer_desc* d, bool linear, const void* x, const floa
     if (math == BBB_MATH_AUTO) math = bbb::tc_supported(*d, g) ? BBB_MATH_BF16_TC : BBB_MATH_FP32;
     if (math == BBB_MATH_BF16_TC) {
         if (!bbb::tc_supported(*d, g)) return fail(BBB_E_UNSUPPORTED, "BBB_MATH_BF16_TC: shape not supported by the tcgen05 path");
+        const size_t need = kTcOffset + bbb::tc_workspace_bytes(g);
+        if (!ws || ws_bytes < need) return fail(BBB_E_WORKSPACE, "workspace too small for the tcgen05 path: need %zu bytes", need);
         bbb::TcArgs a;
+        a.wtiles = (__nv_bfloat16*)((char*)ws + kTcOffset);
+        a.bias_ws = (float*)((char*)ws + kTcOffset + (size_t)bbb::tc_npad(g) * bbb::tc_kpad(g) * 4);
+        a.skip_prep = 0;
         a.g = g; a.x = x; a.w_mu = W_mu; a.w_rho = W_rho; a.b_mu = bias_mu; a.b_rho = bias_rho;
         a.y = y; a.kl_out = kl_out; a.act_std = act_std; a.eps_a = eps_a; a.eps_b = eps_b;
         a.key = bbb::make_key(seed, stream_id); a.stream_base = (const unsigned long long*)stream_base;
@@ -127,8 +133,10 @@ int backward_impl(const bbb_layer_desc* d, bool linear, const void* x, const voi
 extern "C" {
 
 size_t bbb_workspace_bytes(const bbb_layer_desc* desc) {
-    (void)desc;
-    return kBaseWorkspace;
+    if (!desc || desc->math == BBB_MATH_FP32) return kBaseWorkspace;
+    bbb::Geom g;
+    if (!bbb::make_geom(*desc, g)) return kBaseWorkspace;
+    return kTcOffset + bbb::tc_workspace_bytes(g);
 }
 
 int bbb_conv2d_forward(const bbb_layer_desc* desc, const void* x, const float* W_mu, const float* W_rho,

@@ -1,7 +1,38 @@
-// tcgen05 path (placeholder until the UMMA kernel lands).
+// Bayesian layer forward on the 5th-gen tensor cores (BBB_MATH_BF16_TC).
+//
+// Two kernels per layer call:
+//
+//  (P) weight_prep_kernel  -- HBM-bound, touches every parameter exactly once:
+//      sigma = log1p(exp(rho)); closed-form KL reduced to one scalar; BBB: draws eps
+//      (external or Philox) and forms W = mu + eps*sigma, LRT: forms (mu, sigma^2);
+//      writes bf16 operand tiles to the workspace ALREADY IN the canonical UMMA
+//      K-major core-matrix order, one contiguous 8 KB (BBB) / 16 KB (LRT) block per
+//      (n-tile, k-block), so the GEMM kernel stages them with a single bulk-TMA copy.
+//      Doing this once per weight instead of once per M-tile CTA removes a
+//      (#M-tiles)x redundant softplus/Philox (64x for AlexNet conv2 at B=512).  It
+//      depends on the parameters only, so in a captured graph it runs on a side
+//      branch, off the activation critical path.
+//
+//  (G) gemm_tc_kernel  -- implicit-GEMM conv / linear on tcgen05:
+//      warps 0-3 : A producers -- gather the im2col rows of x (fp32 NCHW), convert to
+//                  bf16 (LRT: also x^2), st.shared into the canonical K-major layout,
+//                  fence.proxy.async, mbarrier arrive; afterwards the same warps run
+//                  the epilogue (tcgen05.ld -> bias / sqrt(var)*eps -> NCHW store)
+//      warp 4    : one elected thread issues tcgen05.mma (M=128, N=64, K=16, bf16 ->
+//                  fp32 in TMEM; LRT: second accumulator for the variance path) and
+//                  tcgen05.commit to release smem stages / publish the accumulator
+//      warp 5    : one elected thread stages the prepared weight tiles with
+//                  cp.async.bulk (TMA, mbarrier complete_tx)
+//
+// Replaces layers/BBB/BBBConv.py:61-83, BBB/BBBLinear.py:54-76,
+// BBB_LRT/BBBConv.py:62-87, BBB_LRT/BBBLinear.py:56-79, metrics.py:27-29.
 #pragma once
+#include <cuda_bf16.h>
 #include "common.cuh"
+#include "fwd_simt.cuh"   // apply_act
+
 namespace bbb {
+
 struct TcArgs {
     Geom g;
     const void* x; const float* w_mu; const float* w_rho; const float* b_mu; const float* b_rho;
@@ -11,7 +42,407 @@ struct TcArgs {
     double* kl_partials; unsigned int* kl_counter;
     float prior_mu, prior_sigma;
     int sample, kl_convention, has_bias, act, act_dtype, variant;
+    // prepared-operand workspace
+    __nv_bfloat16* wtiles;   // [n_tiles][k_blocks][planes][64*64]
+    float* bias_ws;          // [2][Npad]: row 0 = bias (BBB: sampled; LRT: mu), row 1 = LRT sigma_b^2
+    int n_tiles, k_blocks, planes;
+    int skip_prep;
 };
-inline bool tc_supported(const bbb_layer_desc&, const Geom&) { return false; }
-inline cudaError_t launch_fwd_tc(const TcArgs&, cudaStream_t, int, int* nl) { *nl = 0; return cudaErrorNotSupported; }
+
+constexpr int TC_BM = 128, TC_BN = 64, TC_BK = 64;
+constexpr int TC_TILE_ELEMS = TC_BN * TC_BK;                 // 4096 bf16 = 8 KB
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;                // 16 KB
+constexpr int TC_B_BYTES = TC_BN * TC_BK * 2;                // 8 KB
+constexpr int TC_SMEM_LIMIT = 227 * 1024;
+
+inline int tc_planes(int variant, int sample) { return (variant == BBB_VARIANT_LRT && sample) ? 2 : 1; }
+inline size_t tc_stage_bytes(int planes) { return (size_t)planes * (TC_A_BYTES + TC_B_BYTES); }
+inline int tc_kpad(const Geom& g) { return (g.K + TC_BK - 1) / TC_BK * TC_BK; }
+inline int tc_npad(const Geom& g) { return (g.N + TC_BN - 1) / TC_BN * TC_BN; }
+inline size_t tc_fixed_smem(const Geom& g) { return 2048 /*two 1 KB alignment slacks*/ + 256 /*barriers*/ + (size_t)tc_kpad(g) * 8; }
+inline int tc_stages(const Geom& g, int planes) {
+    const long avail = (long)TC_SMEM_LIMIT - (long)tc_fixed_smem(g);
+    long s = avail / (long)tc_stage_bytes(planes);
+    if (s > 4) s = 4;
+    return (int)s;
+}
+inline size_t tc_workspace_bytes(const Geom& g) {
+    return (size_t)tc_npad(g) * tc_kpad(g) * 2 /*planes*/ * 2 /*bf16*/ + (size_t)2 * tc_npad(g) * 4;
+}
+inline bool tc_supported(const bbb_layer_desc& d, const Geom& g) {
+    if (d.act_dtype != BBB_DTYPE_F32) return false;
+    if (g.M < 1 || g.N < 1) return false;
+    if (tc_stages(g, 2) < 2) return false;
+    if ((long)tc_npad(g) / TC_BN * (tc_kpad(g) / TC_BK) > 1 << 20) return false;
+    return true;
+}
+
+// ------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, SWIZZLE_NONE ("interleave") shared-memory matrix descriptor (sm_100):
+//   [0,14)  start address >> 4        [16,30) leading-dim byte offset >> 4 (stride between
+//   the two 16-byte K chunks of one MMA)  [32,46) stride-dim byte offset >> 4 (stride between
+//   8-row core-matrix groups)          [46,48) version = 1            [61,64) layout = 0
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
+           ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+// kind::f16 instruction descriptor: c_format=F32 [4,6), a/b_format=BF16 [7,10)/[10,13), K-major A and B,
+// N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// ------------------------------------------------------------ (P) weight prep
+// One CTA per (n-tile, k-block) 64x64 tile (grid-stride).  256 threads: item = (row, 8-wide
+// K chunk); consecutive threads take consecutive rows so the 16-byte writes are contiguous.
+template <int VARIANT>
+__global__ void __launch_bounds__(256)
+weight_prep_kernel(const TcArgs p) {
+    __shared__ double red[32];
+    constexpr bool LRT = VARIANT == BBB_VARIANT_LRT;
+    const Geom& g = p.g;
+    const NoiseKey nkey = effective_key(p.key, p.stream_base);
+    const bool stoch = p.sample != 0;
+    const bool do_kl = p.kl_out != nullptr;
+    const int n_items = p.n_tiles * p.k_blocks;
+    const int npad = p.n_tiles * TC_BN;
+    double kl_acc = 0.0;
+
+    for (int tile = blockIdx.x; tile < n_items; tile += gridDim.x) {
+        const int nt = tile / p.k_blocks, kb = tile - nt * p.k_blocks;
+        __nv_bfloat16* dst = p.wtiles + (size_t)tile * p.planes * TC_TILE_ELEMS;
+        for (int item = threadIdx.x; item < TC_BN * (TC_BK / 8); item += blockDim.x) {
+            const int row = item & (TC_BN - 1), chunk = item >> 6;
+            const int n = nt * TC_BN + row, k0 = kb * TC_BK + chunk * 8;
+            float w[8], s2[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int k = k0 + e;
+                float wv = 0.0f, sv = 0.0f;
+                if (n < g.N && k < g.K) {
+                    const size_t wi = (size_t)n * g.K + k;
+                    const float mu = __ldg(p.w_mu + wi);
+                    float sigma = 0.0f;
+                    if (stoch || do_kl) sigma = softplus_sigma(__ldg(p.w_rho + wi));
+                    if (LRT) { wv = mu; sv = sigma * sigma; }
+                    else if (stoch) {
+                        const float e_ = p.eps_a ? __ldg(p.eps_a + wi) : normal1(wi, nkey);
+                        wv = mu + e_ * sigma;
+                    } else wv = mu;
+                    if (do_kl) kl_acc += (double)kl_term(mu, sigma, p.prior_mu, p.prior_sigma, p.kl_convention);
+                }
+                w[e] = wv; s2[e] = sv;
+            }
+            // canonical K-major core-matrix order inside the 8 KB tile: chunk*1024 + row*16 bytes
+            uint4 o = make_uint4(pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]), pack_bf16(w[4], w[5]), pack_bf16(w[6], w[7]));
+            *reinterpret_cast<uint4*>(dst + chunk * (TC_BN * 8) + row * 8) = o;
+            if (p.planes == 2) {
+                uint4 o2 = make_uint4(pack_bf16(s2[0], s2[1]), pack_bf16(s2[2], s2[3]), pack_bf16(s2[4], s2[5]), pack_bf16(s2[6], s2[7]));
+                *reinterpret_cast<uint4*>(dst + TC_TILE_ELEMS + chunk * (TC_BN * 8) + row * 8) = o2;
+            }
+        }
+        if (kb == 0 && threadIdx.x < TC_BN) {                     // bias slice of this n-tile
+            const int n = nt * TC_BN + threadIdx.x;
+            float bm = 0.0f, bv = 0.0f;
+            if (p.has_bias && n < g.N) {
+                const float mu = __ldg(p.b_mu + n);
+                const float sigma = (stoch || do_kl) ? softplus_sigma(__ldg(p.b_rho + n)) : 0.0f;
+                if (LRT) { bm = mu; bv = sigma * sigma; }
+                else if (stoch) {
+                    const float e_ = p.eps_b ? __ldg(p.eps_b + n) : normal1((uint64_t)g.N * g.K + n, nkey);
+                    bm = mu + e_ * sigma;
+                } else bm = mu;
+                if (do_kl) kl_acc += (double)kl_term(mu, sigma, p.prior_mu, p.prior_sigma, p.kl_convention);
+            }
+            p.bias_ws[n] = bm;
+            p.bias_ws[npad + n] = bv;
+        }
+    }
+    if (do_kl) {
+        const double tot = block_sum(kl_acc, red);
+        if (threadIdx.x == 0) kl_publish(tot, blockIdx.x, gridDim.x, p.kl_partials, p.kl_counter, p.kl_out);
+    }
+}
+
+// ----------------------------------------------------------------- (G) GEMM
+struct TcSmem {      // barrier block at the start of dynamic smem (after 1024-alignment)
+    unsigned long long full[4], empty[4], accum;
+    uint32_t tmem_base, pad;
+};
+
+template <int VARIANT>
+__global__ void __launch_bounds__(192, 1)
+gemm_tc_kernel(const TcArgs p, const int stages) {
+    constexpr bool LRT = VARIANT == BBB_VARIANT_LRT;
+    extern __shared__ uint8_t smem_raw[];
+    const Geom& g = p.g;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int planes = p.planes;                       // 2 only for LRT && sample
+    const bool two = LRT && planes == 2;
+
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - raw);
+    TcSmem* ctl = reinterpret_cast<TcSmem*>(sm);
+    int2* ktab = reinterpret_cast<int2*>(sm + 256);
+    const int kpad = p.k_blocks * TC_BK;
+    const uint32_t tiles_off = (256u + (uint32_t)kpad * 8u + 1023u) & ~1023u;
+    const uint32_t stage_bytes = (uint32_t)planes * (TC_A_BYTES + TC_B_BYTES);
+    // stage layout: [A (16K)] [A^2 (16K, LRT)] [B planes (8K each)]
+    const uint32_t a_off = 0, a2_off = TC_A_BYTES, b_off = (uint32_t)planes * TC_A_BYTES;
+
+    const int n_tile = blockIdx.x, m_tile = blockIdx.y;
+    const int m0 = m_tile * TC_BM, n0 = n_tile * TC_BN;
+
+    // ---- one-time setup ------------------------------------------------------
+    for (int k = threadIdx.x; k < kpad; k += blockDim.x) {
+        int2 e;
+        if (k < g.K) {
+            const int c = k / g.KHW, rs = k - c * g.KHW;
+            const int r = rs / g.KW, s = rs - r * g.KW;
+            e.x = c * g.HW + r * g.DH * g.W + s * g.DW;
+            e.y = ((r * g.DH) << 16) | (s * g.DW);
+        } else { e.x = 0; e.y = 0x7fff7fff; }
+        ktab[k] = e;
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(smem_u32(&ctl->full[s]), 128 + 1);      // 128 A-producer threads + the TMA thread
+            mbar_init(smem_u32(&ctl->empty[s]), 1);           // one tcgen05.commit
+        }
+        mbar_init(smem_u32(&ctl->accum), 1);
+        fence_barrier_init();
+    }
+    const uint32_t tmem_cols = two ? 128u : 64u;
+    if (warp == 4) tmem_alloc(smem_u32(&ctl->tmem_base), tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = ctl->tmem_base;
+
+    if (warp < 4) {
+        // ================= A producers (then epilogue) =========================
+        const int t = threadIdx.x;                      // row of the tile == TMEM lane
+        const int m = m0 + t;
+        const bool mvalid = m < g.M;
+        int ih0 = 0, iw0 = 0; long xb = 0;
+        int bimg = 0, pix = 0;
+        if (mvalid) {
+            bimg = m / g.OHW; pix = m - bimg * g.OHW;
+            const int oh = pix / g.OW, ow = pix - oh * g.OW;
+            ih0 = oh * g.SH - g.PH; iw0 = ow * g.SW - g.PW;
+            xb = (long)bimg * g.Cin * g.HW + (long)ih0 * g.W + iw0;
+        }
+        const float* __restrict__ xp = reinterpret_cast<const float*>(p.x);
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+            const int s = kb % stages;
+            const uint32_t ph = (uint32_t)(kb / stages) & 1u;
+            mbar_wait(smem_u32(&ctl->empty[s]), ph ^ 1u);
+            uint8_t* st = sm + tiles_off + (size_t)s * stage_bytes;
+#pragma unroll 2
+            for (int c8 = 0; c8 < 8; ++c8) {
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int2 kt = ktab[kb * TC_BK + c8 * 8 + e];
+                    const int ih = ih0 + (kt.y >> 16), iw = iw0 + (kt.y & 0xffff);
+                    float val = 0.0f;
+                    if (mvalid && (unsigned)ih < (unsigned)g.H && (unsigned)iw < (unsigned)g.W)
+                        val = __ldg(xp + xb + kt.x);
+                    v[e] = val;
+                }
+                const uint4 o = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                *reinterpret_cast<uint4*>(st + a_off + c8 * (TC_BM * 16) + t * 16) = o;
+                if (two) {
+                    const uint4 o2 = make_uint4(pack_bf16(v[0] * v[0], v[1] * v[1]), pack_bf16(v[2] * v[2], v[3] * v[3]),
+                                                pack_bf16(v[4] * v[4], v[5] * v[5]), pack_bf16(v[6] * v[6], v[7] * v[7]));
+                    *reinterpret_cast<uint4*>(st + a2_off + c8 * (TC_BM * 16) + t * 16) = o2;
+                }
+            }
+            fence_proxy_async();                        // generic-proxy stores -> visible to the tensor core
+            mbar_arrive(smem_u32(&ctl->full[s]));
+        }
+
+        // ================= epilogue ============================================
+        mbar_wait(smem_u32(&ctl->accum), 0u);
+        tc_fence_after();
+        const NoiseKey nkey = effective_key(p.key, p.stream_base);
+        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+        const int npad = p.n_tiles * TC_BN;
+        float* __restrict__ y = reinterpret_cast<float*>(p.y);
+#pragma unroll 1
+        for (int c0 = 0; c0 < TC_BN; c0 += 16) {
+            float am[16], av[16];
+            tmem_ld16(lane_base + (uint32_t)c0, am);
+            if (two) tmem_ld16(lane_base + 64u + (uint32_t)c0, av);
+            if (mvalid) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int n = n0 + c0 + j;
+                    if (n < g.N) {
+                        const size_t o = ((size_t)bimg * g.N + n) * g.OHW + pix;
+                        float val = am[j] + p.bias_ws[n];
+                        if (two) {
+                            const float var = 1e-16f + (av[j] + p.bias_ws[npad + n]);
+                            const float sd = sqrtf(var);
+                            const float e_ = p.eps_a ? __ldg(p.eps_a + o) : normal1(o, nkey);
+                            val = val + sd * e_;
+                            if (p.act_std) p.act_std[o] = sd;
+                        }
+                        y[o] = apply_act(val, p.act);
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    } else if (warp == 4) {
+        // ================= MMA issuer ==========================================
+        constexpr uint32_t idesc = make_idesc_bf16(TC_BM, TC_BN);
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+            const int s = kb % stages;
+            const uint32_t ph = (uint32_t)(kb / stages) & 1u;
+            mbar_wait(smem_u32(&ctl->full[s]), ph);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t st = base + tiles_off + (uint32_t)s * stage_bytes;
+#pragma unroll
+                for (int j = 0; j < TC_BK / 16; ++j) {
+                    const uint64_t da = make_smem_desc(st + a_off + j * 2 * (TC_BM * 16), TC_BM * 16, 128);
+                    const uint64_t db = make_smem_desc(st + b_off + j * 2 * (TC_BN * 16), TC_BN * 16, 128);
+                    umma_bf16(tmem, da, db, idesc, (kb | j) ? 1u : 0u);
+                    if (two) {
+                        const uint64_t da2 = make_smem_desc(st + a2_off + j * 2 * (TC_BM * 16), TC_BM * 16, 128);
+                        const uint64_t db2 = make_smem_desc(st + b_off + TC_B_BYTES + j * 2 * (TC_BN * 16), TC_BN * 16, 128);
+                        umma_bf16(tmem + 64u, da2, db2, idesc, (kb | j) ? 1u : 0u);
+                    }
+                }
+                umma_commit(smem_u32(&ctl->empty[s]));            // frees the smem stage when the MMAs retire
+                if (kb == p.k_blocks - 1) umma_commit(smem_u32(&ctl->accum));
+            }
+            __syncwarp();
+        }
+        tc_fence_before();
+    } else {
+        // ================= weight-tile TMA ======================================
+        if (lane == 0) {
+            const uint32_t bytes = (uint32_t)planes * TC_B_BYTES;
+            const __nv_bfloat16* src0 = p.wtiles + (size_t)n_tile * p.k_blocks * planes * TC_TILE_ELEMS;
+            for (int kb = 0; kb < p.k_blocks; ++kb) {
+                const int s = kb % stages;
+                const uint32_t ph = (uint32_t)(kb / stages) & 1u;
+                mbar_wait(smem_u32(&ctl->empty[s]), ph ^ 1u);
+                const uint32_t bar = smem_u32(&ctl->full[s]);
+                mbar_arrive_expect_tx(bar, bytes);
+                bulk_g2s(base + tiles_off + (uint32_t)s * stage_bytes + b_off, src0 + (size_t)kb * planes * TC_TILE_ELEMS, bytes, bar);
+            }
+        }
+    }
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 4) tmem_dealloc(tmem, tmem_cols);
+}
+
+inline cudaError_t launch_fwd_tc(TcArgs a, cudaStream_t st, int n_sm, int* n_launch) {
+    const Geom& g = a.g;
+    a.planes = tc_planes(a.variant, a.sample);
+    a.n_tiles = tc_npad(g) / TC_BN;
+    a.k_blocks = tc_kpad(g) / TC_BK;
+    *n_launch = 0;
+    const bool lrt = a.variant == BBB_VARIANT_LRT;
+    if (!a.skip_prep) {
+        int grid = a.n_tiles * a.k_blocks;
+        if (grid > 2048) grid = 2048;
+        if (lrt) weight_prep_kernel<BBB_VARIANT_LRT><<<grid, 256, 0, st>>>(a);
+        else     weight_prep_kernel<BBB_VARIANT_BBB><<<grid, 256, 0, st>>>(a);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        *n_launch += 1;
+        a.kl_out = nullptr;
+    }
+    const int stages = tc_stages(g, a.planes);
+    const size_t smem = tc_fixed_smem(g) + (size_t)stages * tc_stage_bytes(a.planes);
+    dim3 grid(a.n_tiles, (g.M + TC_BM - 1) / TC_BM);
+    cudaError_t e;
+    if (lrt) {
+        e = cudaFuncSetAttribute(gemm_tc_kernel<BBB_VARIANT_LRT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        gemm_tc_kernel<BBB_VARIANT_LRT><<<grid, 192, smem, st>>>(a, stages);
+    } else {
+        e = cudaFuncSetAttribute(gemm_tc_kernel<BBB_VARIANT_BBB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        gemm_tc_kernel<BBB_VARIANT_BBB><<<grid, 192, smem, st>>>(a, stages);
+    }
+    (void)n_sm;
+    e = cudaGetLastError();
+    if (e == cudaSuccess) *n_launch += 1;
+    return e;
+}
+
 }  // namespace bbb

@@ -121,13 +121,15 @@ def _require_cuda(t: torch.Tensor, what: str):
 _ws_cache: dict = {}
 
 
-def workspace(device) -> torch.Tensor:
-    """Zero-initialised scratch, one per (device, stream): calls on one stream are
-    ordered, so sharing it is safe; the kernels leave it zeroed."""
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+def workspace(device, desc=None, owner=None) -> torch.Tensor:
+    """Zero-initialised scratch.  Without `owner`: one per (device, stream) -- calls on
+    one stream are ordered, so sharing is safe and the kernels leave the counters
+    zeroed.  With `owner` (a layer): a private buffer sized by bbb_workspace_bytes(desc),
+    which on the tcgen05 path also holds that layer's prepared bf16 operand tiles."""
+    n = int(L.lib().bbb_workspace_bytes(C.byref(desc) if desc is not None else None))
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream, owner)
     ws = _ws_cache.get(key)
-    if ws is None:
-        n = int(L.lib().bbb_workspace_bytes(None))
+    if ws is None or ws.numel() < n:
         ws = torch.zeros(n, dtype=torch.uint8, device=device)
         _ws_cache[key] = ws
     return ws
@@ -210,7 +212,7 @@ class BayesLayerFn(torch.autograd.Function):
         act_std = None
         if variant == L.VARIANT_LRT and sample and need_grad:
             act_std = torch.empty(yshape, dtype=torch.float32, device=dev)
-        ws = workspace(dev)
+        ws = workspace(dev, d, cfg.get("owner"))
         fn = lib.bbb_linear_forward if conv is None else lib.bbb_conv2d_forward
         rc = fn(C.byref(d), _ptr(x), _ptr(W_mu_c), _ptr(W_rho_c), _ptr(bias_mu), _ptr(bias_rho),
                 _ptr(y), _ptr(kl), _ptr(act_std), _ptr(eps_a), _ptr(eps_b),

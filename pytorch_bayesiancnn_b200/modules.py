@@ -126,6 +126,7 @@ class _BayesLayer(ModuleWrapper):
             "math": L.MATH_BY_NAME[self.math],
             "kl_convention": L.KL_BY_NAME[self.kl_convention],
             "act": L.ACT_NONE,
+            "owner": id(self),
         }
 
     def forward(self, x, sample=True):

@@ -212,3 +212,110 @@ def test_errors_are_loud(dev):
         layer(torch.randn(1, 5, 8, 8, device=dev))      # channel mismatch
     with pytest.raises(bbb.EngineError):
         layer(torch.randn(1, 3, 2, 2, device=dev))      # kernel larger than input
+
+
+# --------------------------------------------------------------------------- #
+# tcgen05 path (math='bf16'): bf16 operands, fp32 accumulate -> 1e-2 bar
+# --------------------------------------------------------------------------- #
+BF16_TOL = 1e-2
+
+
+def test_tc_layer_cases_external_eps(golden_layers, dev):
+    import pytorch_bayesiancnn_b200 as bbb
+    worst = 0.0
+    for name in case_names(golden_layers):
+        c = load_case(golden_layers, name)
+        layer = build_layer_from_case(name, c, dev).train()
+        layer.set_flag("math", "bf16")
+        eps = [c["eps_w"]] + ([c["eps_b"]] if "eps_b" in c else []) if "_bbb_" in name else [c["eps_y"]]
+        with torch.no_grad(), bbb.external_eps(eps):
+            y = layer(c["x"].to(dev))
+            kl = layer.kl_loss()
+        e = scale_err(y, c["y"])
+        worst = max(worst, e)
+        assert e < BF16_TOL, (name, e)
+        assert abs(float(kl) - float(c["kl"])) <= KL_TOL * abs(float(c["kl"])), (name, float(kl), float(c["kl"]))
+        layer.eval()
+        with torch.no_grad():
+            ym = layer(c["x"].to(dev), sample=False)
+        assert scale_err(ym, c["y_mean"]) < BF16_TOL, name
+    print("tc layer cases worst scale err", worst)
+
+
+def test_tc_alexnet_layer_shapes_b512(dev):
+    """Every BBBAlexNet layer geometry at the BASELINE batch (512), both variants,
+    tcgen05 path vs the oracle on identical eps."""
+    import pytorch_bayesiancnn_b200 as bbb
+    from oracle import bbb_oracle as O
+    torch.set_num_threads(max(1, (torch.get_num_threads())))
+    geoms = [(3, 64, 11, 4, 5, 32), (64, 192, 5, 1, 2, 4), (192, 384, 3, 1, 1, 2), (384, 256, 3, 1, 1, 2),
+             (256, 128, 3, 1, 1, 2)]
+    g = torch.Generator().manual_seed(11)
+    for variant, cls in (("bbb", bbb.BBB_Conv2d), ("lrt", bbb.BBB_LRT_Conv2d)):
+        for (cin, cout, k, s, p, hw) in geoms:
+            torch.manual_seed(cin)
+            layer = cls(cin, cout, k, stride=s, padding=p, priors=CFG_PRIORS).to(dev).train()
+            layer.set_flag("math", "bf16")
+            x = torch.rand(512, cin, hw, hw, generator=g) * 2
+            P = [t.detach().cpu() for t in (layer.W_mu, layer.W_rho, layer.bias_mu, layer.bias_rho)]
+            ho = (hw + 2 * p - k) // s + 1
+            if variant == "bbb":
+                eps = [torch.randn(P[0].shape, generator=g), torch.randn(cout, generator=g)]
+                ref = O.bbb_forward(x, *P, eps[0], eps[1], (s, p, 1))
+            else:
+                eps = [torch.randn(512, cout, ho, ho, generator=g)]
+                ref = O.lrt_forward(x, *P, eps[0], (s, p, 1))
+            with torch.no_grad(), bbb.external_eps(eps):
+                y = layer(x.to(dev))
+                kl = float(layer.kl_loss())
+            e = scale_err(y, ref)
+            refkl = float(O.kl_loss(*P, 0.0, 0.1))
+            assert e < BF16_TOL, (variant, cin, cout, e)
+            assert abs(kl - refkl) <= KL_TOL * abs(refkl)
+            # and the IEEE-fp32 CUDA-core path on the same inputs
+            layer.set_flag("math", "fp32")
+            with torch.no_grad(), bbb.external_eps(eps):
+                y32 = layer(x.to(dev))
+            assert scale_err(y32, ref) < FP32_TOL, (variant, cin, cout, scale_err(y32, ref))
+
+
+def test_tc_model_cases_external_eps(golden_models, dev):
+    import pytorch_bayesiancnn_b200 as bbb
+    from pytorch_bayesiancnn_b200 import models as M
+    from oracle import bbb_oracle as O
+    cls = {"alexnet": M.BBBAlexNet, "lenet": M.BBBLeNet, "3conv3fc": M.BBB3Conv3FC}
+    for name in case_names(golden_models):
+        c = load_case(golden_models, name)
+        key, inputs, outputs, variant, act, batch = [str(v) for v in c["meta"]]
+        inputs, outputs, batch = int(inputs), int(outputs), int(batch)
+        params = O.init_params(key, outputs, inputs, CFG_PRIORS, seed=123)
+        net = load_params_into(cls[key](outputs, inputs, CFG_PRIORS, variant, act), params).to(dev).train()
+        net.set_flag("math", "bf16")
+        eps = O.draw_eps_like_reference(O.eps_shapes(key, outputs, inputs, variant, batch), seed=7)
+        with torch.no_grad(), bbb.external_eps(eps):
+            logits, kl = net(c["x"].to(dev))
+        e = scale_err(logits, c["logits"])
+        print(name, "bf16 chain scale err", e)
+        assert e < 2 * BF16_TOL, (name, e)      # six bf16 layers chained; per-layer bar is 1e-2
+        assert abs(float(kl) - float(c["kl"])) <= KL_TOL * abs(float(c["kl"])), (name, float(kl), float(c["kl"]))
+
+
+def test_tc_philox_equals_external_draw(dev):
+    import pytorch_bayesiancnn_b200 as bbb
+    for cls in (bbb.BBB_Conv2d, bbb.BBB_LRT_Conv2d):
+        torch.manual_seed(4)
+        layer = cls(16, 96, 3, padding=1, priors=CFG_PRIORS).to(dev).train()
+        layer.set_flag("math", "bf16")
+        x = torch.randn(40, 16, 6, 6, device=dev)
+        bbb.manual_seed(77, 5)
+        with torch.no_grad():
+            y1 = layer(x)
+        if cls is bbb.BBB_Conv2d:
+            nw = layer.W_mu.numel()
+            eps = [bbb.philox_normal(nw, 77, 5, 0, device=dev).view_as(layer.W_mu),
+                   bbb.philox_normal(96, 77, 5, nw, device=dev)]
+        else:
+            eps = [bbb.philox_normal(y1.numel(), 77, 5, 0, device=dev).view_as(y1)]
+        with torch.no_grad(), bbb.external_eps(eps):
+            y2 = layer(x)
+        assert scale_err(y1, y2) < 1e-6
