@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import torch
 
+from . import _lib
 from . import functional as Fn
 
 _STRIDE = 1 << 20      # stream ids one replay may consume (>= Bayesian layer calls per forward)
@@ -36,10 +37,13 @@ class GraphedForward:
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
         with torch.cuda.graph(self.graph), torch.no_grad():
             Fn.noise_advance(self.base, _STRIDE)
             with Fn.stream_base(self.base):
                 self.logits, self.kl = net(self.x)
+        self.kernels_per_replay = _lib.launch_count() - n0     # engine kernels captured in the graph
+        self.replays = 0
         self.reset(self.first_stream)
 
     def reset(self, first_stream: int = 0):
@@ -50,4 +54,5 @@ class GraphedForward:
         if x is not None:
             self.x.copy_(x, non_blocking=non_blocking)
         self.graph.replay()
+        self.replays += 1
         return self.logits, self.kl
