@@ -108,6 +108,31 @@ int bbb_linear_forward(const bbb_layer_desc* desc, const void* x,
                        uint64_t seed, uint64_t stream_id, const uint64_t* stream_base,
                        void* workspace, size_t workspace_bytes, void* cuda_stream);
 
+/* Activation layouts of the fused tcgen05 chain (bbb_layer_forward_fused). */
+enum { BBB_LAYOUT_NCHW_F32 = 0,      /* reference layout: [B, C, H, W] fp32                       */
+       BBB_LAYOUT_PACKED_BF16 = 1,   /* [B, pitch] bf16, column = (h*W + w)*C + c (NHWC flattened) */
+       BBB_LAYOUT_ROWMAJOR_F32 = 2 };/* [B, OH*OW, Cout] fp32 (logits when OH*OW == 1)            */
+
+/* One Bayesian layer of a fused chain: the layer forward + KL (as bbb_conv2d_forward /
+ * bbb_linear_forward) with the model file's activation (desc->epilogue_act) and 2x2/2
+ * max-pool (desc->pool_k == 2) fused into the epilogue, reading and writing the packed
+ * bf16 inter-layer format so the next layer's operand is a plain 2-D TMA box.  Replaces,
+ * per [BBBConv2d|BBBLinear, nn.Softplus|nn.ReLU, nn.MaxPool2d(2,2), FlattenLayer] run of
+ * children in ModuleWrapper.forward (layers/misc.py:16-18; BayesianAlexNet.py:34-53).
+ *   x, x_sq  : input and (LRT, packed input only) its element-wise square
+ *   in_pitch : elements per row of a packed input;  prev_hw: for a linear layer fed by a
+ *              flattened HxW map, H*W of that map (reference feature order is c*HW + pix)
+ *   y, y_sq  : output and (packed output, nullable) its square for a following LRT layer
+ * Forward only (math = BBB_MATH_BF16_TC); eps / Philox / KL semantics as the unfused calls. */
+int bbb_layer_forward_fused(const bbb_layer_desc* desc,
+                            const void* x, const void* x_sq, int32_t in_layout, int32_t in_pitch, int32_t prev_hw,
+                            const float* W_mu, const float* W_rho,
+                            const float* bias_mu, const float* bias_rho,
+                            void* y, void* y_sq, int32_t out_layout, int32_t out_pitch,
+                            float* kl_out, const float* eps_a, const float* eps_b,
+                            uint64_t seed, uint64_t stream_id, const uint64_t* stream_base,
+                            void* workspace, size_t workspace_bytes, void* cuda_stream);
+
 /* Replaces layer.kl_loss() -> metrics.calculate_kl (metrics.py:27-29 with the call
  * binding of layers/BBB/BBBConv.py:80-82) when no forward preceded it: sigma is
  * recomputed from rho.  n_w = |W|, n_b = |bias| (0 if none). */

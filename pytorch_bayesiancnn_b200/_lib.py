@@ -18,13 +18,14 @@ DTYPE_F32, DTYPE_BF16 = 0, 1
 MATH_FP32, MATH_BF16_TC, MATH_AUTO = 0, 1, 2
 KL_REFERENCE, KL_TEXTBOOK = 0, 1
 ACT_NONE, ACT_SOFTPLUS, ACT_RELU = 0, 1, 2
+LAYOUT_NCHW_F32, LAYOUT_PACKED_BF16, LAYOUT_ROWMAJOR_F32 = 0, 1, 2
 
 MATH_BY_NAME = {"fp32": MATH_FP32, "bf16": MATH_BF16_TC, "auto": MATH_AUTO}
 KL_BY_NAME = {"reference": KL_REFERENCE, "textbook": KL_TEXTBOOK}
 ACT_BY_NAME = {None: ACT_NONE, "none": ACT_NONE, "softplus": ACT_SOFTPLUS, "relu": ACT_RELU}
 
 SYMBOLS = (
-    "bbb_workspace_bytes", "bbb_conv2d_forward", "bbb_linear_forward", "bbb_kl_forward",
+    "bbb_workspace_bytes", "bbb_conv2d_forward", "bbb_linear_forward", "bbb_layer_forward_fused", "bbb_kl_forward",
     "bbb_kl_backward", "bbb_conv2d_backward", "bbb_linear_backward", "bbb_philox_normal_fill",
     "bbb_mc_combine", "bbb_noise_advance", "bbb_last_error", "bbb_abi_version", "bbb_launch_count",
 )
@@ -60,6 +61,9 @@ def _bind(lib):
     for name in ("bbb_conv2d_backward", "bbb_linear_backward"):
         getattr(lib, name).argtypes = bwd
         getattr(lib, name).restype = C.c_int
+    lib.bbb_layer_forward_fused.argtypes = [dp, vp, vp, i32, i32, i32, fp, fp, fp, fp, vp, vp, i32, i32, fp, fp, fp,
+                                            u64, u64, vp, vp, sz, vp]
+    lib.bbb_layer_forward_fused.restype = C.c_int
     lib.bbb_kl_forward.argtypes = [fp, fp, u64, fp, fp, u64, C.c_float, C.c_float, i32, fp, vp, sz, vp]
     lib.bbb_kl_forward.restype = C.c_int
     lib.bbb_kl_backward.argtypes = [fp, fp, u64, C.c_float, C.c_float, i32, fp, fp, fp, vp]

@@ -9,6 +9,7 @@
 #include "misc_kernels.cuh"
 #include "bwd_simt.cuh"
 #include "fwd_tc.cuh"
+#include "fused_tc.cuh"
 
 namespace {
 
@@ -70,7 +71,7 @@ int forward_impl(const bbb_layer_desc* d, bool linear, const void* x, const floa
         bbb::TcArgs a;
         a.wtiles = (__nv_bfloat16*)((char*)ws + kTcOffset);
         a.bias_ws = (float*)((char*)ws + kTcOffset + (size_t)bbb::tc_npad(g) * bbb::tc_kpad(g) * 4);
-        a.skip_prep = 0;
+        a.skip_prep = 0; a.y_sq = nullptr; a.out_mode = 2; a.out_pitch = 0; a.pool = 0;
         a.g = g; a.x = x; a.w_mu = W_mu; a.w_rho = W_rho; a.b_mu = bias_mu; a.b_rho = bias_rho;
         a.y = y; a.kl_out = kl_out; a.act_std = act_std; a.eps_a = eps_a; a.eps_b = eps_b;
         a.key = bbb::make_key(seed, stream_id); a.stream_base = (const unsigned long long*)stream_base;
@@ -136,7 +137,8 @@ size_t bbb_workspace_bytes(const bbb_layer_desc* desc) {
     if (!desc || desc->math == BBB_MATH_FP32) return kBaseWorkspace;
     bbb::Geom g;
     if (!bbb::make_geom(*desc, g)) return kBaseWorkspace;
-    return kTcOffset + bbb::tc_workspace_bytes(g);
+    const size_t a = bbb::tc_workspace_bytes(g), b = bbb::fused_workspace_bytes(g);
+    return kTcOffset + (a > b ? a : b);
 }
 
 int bbb_conv2d_forward(const bbb_layer_desc* desc, const void* x, const float* W_mu, const float* W_rho,
@@ -173,6 +175,67 @@ int bbb_linear_backward(const bbb_layer_desc* desc, const void* x, const void* g
     return backward_impl(desc, true, x, grad_y, W_mu, W_rho, bias_mu, bias_rho, act_std, eps_a, eps_b, seed,
                          stream_id, stream_base, grad_x, g_W_mu, g_W_rho, g_bias_mu, g_bias_rho, workspace, workspace_bytes,
                          cuda_stream);
+}
+
+int bbb_layer_forward_fused(const bbb_layer_desc* d, const void* x, const void* x_sq, int32_t in_layout,
+                            int32_t in_pitch, int32_t prev_hw, const float* W_mu, const float* W_rho,
+                            const float* bias_mu, const float* bias_rho, void* y, void* y_sq, int32_t out_layout,
+                            int32_t out_pitch, float* kl_out, const float* eps_a, const float* eps_b, uint64_t seed,
+                            uint64_t stream_id, const uint64_t* stream_base, void* ws, size_t ws_bytes, void* stream) {
+    bbb::Geom g;
+    if (int rc = check_desc(d, g, false)) return rc;
+    if (!x || !W_mu || !W_rho || !y) return fail(BBB_E_INVALID, "NULL tensor pointer");
+    if (d->has_bias && (!bias_mu || !bias_rho)) return fail(BBB_E_INVALID, "has_bias set but bias pointers NULL");
+    if (d->math == BBB_MATH_FP32) return fail(BBB_E_UNSUPPORTED, "the fused chain exists on the tcgen05 (bf16) path only");
+    const int pool = d->pool_k != 0;
+    if (pool && !(d->pool_k == 2 && d->pool_s == 2)) return fail(BBB_E_UNSUPPORTED, "only a 2x2 stride-2 max-pool can be fused");
+    if (pool && ((g.OH | g.OW) & 1)) return fail(BBB_E_UNSUPPORTED, "fused pool needs even output height/width");
+    const size_t need = bbb_workspace_bytes(d);
+    if (!ws || ws_bytes < need) return fail(BBB_E_WORKSPACE, "workspace too small for the fused path: need %zu bytes", need);
+    if (out_layout == BBB_LAYOUT_PACKED_BF16 && (out_pitch % 8 || out_pitch < (pool ? g.OHW / 4 : g.OHW) * g.N))
+        return fail(BBB_E_INVALID, "bad out_pitch %d", out_pitch);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int out_mode = out_layout == BBB_LAYOUT_PACKED_BF16 ? 0 : (out_layout == BBB_LAYOUT_ROWMAJOR_F32 ? 1 : 2);
+    int nl = 0;
+    if (in_layout == BBB_LAYOUT_NCHW_F32) {
+        if (!bbb::tc_supported(*d, g)) return fail(BBB_E_UNSUPPORTED, "shape not supported by the tcgen05 gather path");
+        if (out_mode == 1 && (pool ? g.OHW / 4 : g.OHW) != 1) return fail(BBB_E_UNSUPPORTED, "row-major fp32 output needs a 1x1 map on the gather path");
+        bbb::TcArgs a;
+        a.g = g; a.x = x; a.w_mu = W_mu; a.w_rho = W_rho; a.b_mu = bias_mu; a.b_rho = bias_rho;
+        a.y = y; a.kl_out = kl_out; a.act_std = nullptr; a.eps_a = eps_a; a.eps_b = eps_b;
+        a.key = bbb::make_key(seed, stream_id); a.stream_base = (const unsigned long long*)stream_base;
+        a.kl_counter = (unsigned int*)ws; a.kl_partials = (double*)((char*)ws + kCounterBytes);
+        a.prior_mu = d->prior_mu; a.prior_sigma = d->prior_sigma;
+        a.sample = d->sample; a.kl_convention = d->kl_convention; a.has_bias = d->has_bias; a.act = d->epilogue_act;
+        a.act_dtype = d->act_dtype; a.variant = d->variant;
+        a.wtiles = (__nv_bfloat16*)((char*)ws + kTcOffset);
+        a.bias_ws = (float*)((char*)ws + kTcOffset + (size_t)bbb::tc_npad(g) * bbb::tc_kpad(g) * 4);
+        a.skip_prep = 0; a.y_sq = y_sq; a.out_mode = out_mode == 1 ? 2 : out_mode; a.out_pitch = out_pitch; a.pool = pool;
+        cudaError_t e = bbb::launch_fwd_tc(a, st, sm_count(), &nl);
+        if (e != cudaSuccess) return cuda_fail(e, "fused gather launch");
+    } else if (in_layout == BBB_LAYOUT_PACKED_BF16) {
+        if (!bbb::fused_supported(g, pool)) return fail(BBB_E_UNSUPPORTED, "shape not supported by the fused tap-GEMM path");
+        if (in_pitch % 8 || in_pitch < g.HW * g.Cin) return fail(BBB_E_INVALID, "bad in_pitch %d", in_pitch);
+        if (prev_hw < 1 || g.Cin % prev_hw) return fail(BBB_E_INVALID, "bad prev_hw %d", prev_hw);
+        bbb::FusedArgs a;
+        a.g = g; a.variant = d->variant; a.sample = d->sample; a.has_bias = d->has_bias; a.act = d->epilogue_act;
+        a.kl_convention = d->kl_convention; a.prior_mu = d->prior_mu; a.prior_sigma = d->prior_sigma;
+        a.w_mu = W_mu; a.w_rho = W_rho; a.b_mu = bias_mu; a.b_rho = bias_rho; a.eps_a = eps_a; a.eps_b = eps_b;
+        a.key = bbb::make_key(seed, stream_id); a.stream_base = (const unsigned long long*)stream_base;
+        a.kl_counter = (unsigned int*)ws; a.kl_partials = (double*)((char*)ws + kCounterBytes); a.kl_out = kl_out;
+        const size_t cpad = (size_t)(g.N + 63) / 64 * 64, kpad = (size_t)(g.Cin + 63) / 64 * 64;
+        a.wtiles = (__nv_bfloat16*)((char*)ws + kTcOffset);
+        a.bias_ws = (float*)((char*)ws + kTcOffset + cpad * kpad * g.KHW * 4);
+        a.prev_hw = prev_hw; a.y = y; a.y_sq = y_sq; a.out_mode = out_mode; a.out_pitch = out_pitch; a.pool = pool;
+        a.in_pitch = in_pitch;
+        const char* why = "";
+        cudaError_t e = bbb::launch_fused(a, x, x_sq, st, &nl, &why);
+        if (e != cudaSuccess) return fail(BBB_E_CUDA, "fused tap-GEMM launch: %s %s", cudaGetErrorString(e), why);
+    } else {
+        return fail(BBB_E_INVALID, "bad in_layout %d", in_layout);
+    }
+    g_launches += nl;
+    return BBB_OK;
 }
 
 int bbb_kl_forward(const float* W_mu, const float* W_rho, uint64_t n_w, const float* bias_mu,

@@ -1,0 +1,485 @@
+// Fused tcgen05 pipeline for chains of Bayesian layers on small feature maps.
+//
+// Between fused layers the activation lives in HBM as a "packed" bf16 matrix
+// [batch, (pixel, channel)] (NHWC flattened, row pitch padded to 8 elements) plus,
+// for the LRT variant, its element-wise square -- so the next layer's A operand is
+// a plain 2-D TMA box and x^2 never has to be recomputed.
+//
+//  (P) tap_prep_kernel : like weight_prep_kernel but emits the weights tap-major:
+//      [tap][cout block][cin block][plane][NG x 64] bf16 sub-tiles in canonical
+//      K-major core-matrix order.  softplus / eps / KL exactly once per weight.
+//
+//  (G) tap_gemm_kernel : "conv on a small map == block-structured dense layer".
+//      Rows = 128 images, K walks (input pixel, 64-channel block), each output
+//      column group = (output pixel, NG output channels).  For every K step the
+//      tap that links the group's output pixel to the input pixel is computed; if
+//      it falls outside the kernel window the MMA (and the weight copy) is skipped
+//      -- zero padding costs nothing (AlexNet conv3-5: 4 of 9 taps are live).
+//        warp 5 : TMA producer -- cp.async.bulk.tensor.2d for A (and A^2), 128B swizzle;
+//                 cp.async.bulk for the live weight sub-tiles
+//        warp 4 : tcgen05.mma issuer (M=128, N=NG, bf16 -> fp32 TMEM; LRT: 2nd plane)
+//        warps 0-3 : epilogue -- tcgen05.ld, bias, LRT sqrt(var)*eps, 2x2 max-pool across
+//                 the four column groups, activation, packed bf16 (+square) or fp32 store
+#pragma once
+#include <cuda.h>
+#include "fwd_tc.cuh"
+
+namespace bbb {
+
+enum { OUT_PACKED_BF16 = 0, OUT_ROWMAJOR_F32 = 1, OUT_NCHW_F32 = 2 };
+
+struct FusedArgs {
+    Geom g;
+    int variant, sample, has_bias, act, kl_convention;
+    float prior_mu, prior_sigma;
+    const float *w_mu, *w_rho, *b_mu, *b_rho, *eps_a, *eps_b;
+    NoiseKey key; const unsigned long long* stream_base;
+    double* kl_partials; unsigned int* kl_counter; float* kl_out;
+    __nv_bfloat16* wtiles; float* bias_ws;
+    int planes, ng, n_cblk, n_kblk, taps;
+    int prev_hw;                 // linear fed by a flattened HxW map: k' = pix*C + c  <->  ref k = c*HW + pix
+    void* y; void* y_sq;
+    int out_mode, out_pitch, pool, in_pitch;
+};
+
+__host__ __device__ inline size_t fused_wtile_elems(const FusedArgs& a) { return (size_t)a.planes * a.ng * 64; }
+inline size_t fused_workspace_bytes(const Geom& g) {
+    // worst case NG=16 padding of Cout, 2 planes
+    const size_t cpad = (size_t)(g.N + 63) / 64 * 64, kpad = (size_t)(g.Cin + 63) / 64 * 64;
+    return cpad * kpad * g.KHW * 2 * 2 + 2 * cpad * 4;
+}
+
+// ------------------------------------------------------------- (P) tap prep
+template <int VARIANT>
+__global__ void __launch_bounds__(256)
+tap_prep_kernel(const FusedArgs p) {
+    __shared__ double red[32];
+    constexpr bool LRT = VARIANT == BBB_VARIANT_LRT;
+    const Geom& g = p.g;
+    const NoiseKey nkey = effective_key(p.key, p.stream_base);
+    const bool stoch = p.sample != 0, do_kl = p.kl_out != nullptr;
+    const int n_pairs = p.n_cblk * p.n_kblk;
+    const int cprev = g.Cin / p.prev_hw;
+    const size_t sub = fused_wtile_elems(p);
+    double kl_acc = 0.0;
+    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+        const int cb = pair / p.n_kblk, kb = pair - cb * p.n_kblk;
+        for (int tap = 0; tap < p.taps; ++tap) {
+            __nv_bfloat16* dst = p.wtiles + ((size_t)(tap * p.n_cblk + cb) * p.n_kblk + kb) * sub;
+            for (int item = threadIdx.x; item < p.ng * 8; item += blockDim.x) {
+                const int row = item % p.ng, chunk = item / p.ng;
+                const int n = cb * p.ng + row;
+                float w[8], s2[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int kq = kb * 64 + chunk * 8 + e;        // packed input-channel index
+                    float wv = 0.0f, sv = 0.0f;
+                    if (n < g.N && kq < g.Cin) {
+                        const int cin = (p.prev_hw > 1) ? ((kq % cprev) * p.prev_hw + kq / cprev) : kq;
+                        const size_t wi = (size_t)n * g.K + (size_t)cin * g.KHW + tap;
+                        const float mu = __ldg(p.w_mu + wi);
+                        float sigma = 0.0f;
+                        if (stoch || do_kl) sigma = softplus_sigma(__ldg(p.w_rho + wi));
+                        if (LRT) { wv = mu; sv = sigma * sigma; }
+                        else if (stoch) {
+                            const float e_ = p.eps_a ? __ldg(p.eps_a + wi) : normal1(wi, nkey);
+                            wv = mu + e_ * sigma;
+                        } else wv = mu;
+                        if (do_kl) kl_acc += (double)kl_term(mu, sigma, p.prior_mu, p.prior_sigma, p.kl_convention);
+                    }
+                    w[e] = wv; s2[e] = sv;
+                }
+                const uint4 o = make_uint4(pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]), pack_bf16(w[4], w[5]), pack_bf16(w[6], w[7]));
+                *reinterpret_cast<uint4*>(dst + chunk * (p.ng * 8) + row * 8) = o;
+                if (p.planes == 2) {
+                    const uint4 o2 = make_uint4(pack_bf16(s2[0], s2[1]), pack_bf16(s2[2], s2[3]), pack_bf16(s2[4], s2[5]), pack_bf16(s2[6], s2[7]));
+                    *reinterpret_cast<uint4*>(dst + p.ng * 64 + chunk * (p.ng * 8) + row * 8) = o2;
+                }
+            }
+        }
+        if (kb == 0 && threadIdx.x < p.ng) {
+            const int n = cb * p.ng + threadIdx.x;
+            const int npad = p.n_cblk * p.ng;
+            float bm = 0.0f, bv = 0.0f;
+            if (p.has_bias && n < g.N) {
+                const float mu = __ldg(p.b_mu + n);
+                const float sigma = (stoch || do_kl) ? softplus_sigma(__ldg(p.b_rho + n)) : 0.0f;
+                if (LRT) { bm = mu; bv = sigma * sigma; }
+                else if (stoch) {
+                    const float e_ = p.eps_b ? __ldg(p.eps_b + n) : normal1((uint64_t)g.N * g.K + n, nkey);
+                    bm = mu + e_ * sigma;
+                } else bm = mu;
+                if (do_kl) kl_acc += (double)kl_term(mu, sigma, p.prior_mu, p.prior_sigma, p.kl_convention);
+            }
+            p.bias_ws[n] = bm;
+            p.bias_ws[npad + n] = bv;
+        }
+    }
+    if (do_kl) {
+        const double tot = block_sum(kl_acc, red);
+        if (threadIdx.x == 0) kl_publish(tot, blockIdx.x, gridDim.x, p.kl_partials, p.kl_counter, p.kl_out);
+    }
+}
+
+// ------------------------------------------------------------- TMA helpers
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+// K-major SWIZZLE_128B descriptor: 8-row groups 1024 B apart, layout_type = 2 at [61,64)
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           (1ull << 46) | (2ull << 61);
+}
+
+struct FusedSmem {
+    unsigned long long full[4], empty[4], accum;
+    uint32_t tmem_base, pad;
+};
+
+// tap linking output pixel (oh,ow) with input pixel (ih,iw); -1 if outside the kernel window
+__device__ __forceinline__ int tap_of(const Geom& g, int oh, int ow, int ih, int iw) {
+    const int r = ih - oh * g.SH + g.PH, s = iw - ow * g.SW + g.PW;
+    if ((unsigned)r < (unsigned)g.KH && (unsigned)s < (unsigned)g.KW) return r * g.KW + s;
+    return -1;
+}
+
+template <int VARIANT>
+__global__ void __launch_bounds__(192, 1)
+tap_gemm_kernel(const FusedArgs p, const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a2,
+                const int stages) {
+    extern __shared__ uint8_t smem_raw[];
+    const Geom& g = p.g;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int planes = p.planes;
+    const bool two = planes == 2;
+    const int ng = p.ng, groups = 64 / ng;
+
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - raw);
+    FusedSmem* ctl = reinterpret_cast<FusedSmem*>(sm);
+    const uint32_t tiles_off = 1024u;
+    const uint32_t stage_bytes = (uint32_t)planes * (TC_A_BYTES + TC_B_BYTES);
+    const uint32_t a_off = 0, a2_off = TC_A_BYTES, b_off = (uint32_t)planes * TC_A_BYTES;
+    const uint32_t sub_bytes = (uint32_t)planes * ng * 128;          // one weight sub-tile (all planes)
+
+    // output tile -> (pixel set, cout block)
+    const int n_tile = blockIdx.x, m0 = blockIdx.y * TC_BM;
+    const int cb = n_tile % p.n_cblk, pset = n_tile / p.n_cblk;
+    int goh[4], gow[4];
+    if (p.pool) {
+        const int wy = pset / (g.OW >> 1), wx = pset - wy * (g.OW >> 1);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { goh[q] = 2 * wy + (q >> 1); gow[q] = 2 * wx + (q & 1); }
+    } else {
+        goh[0] = pset / g.OW; gow[0] = pset - goh[0] * g.OW;
+#pragma unroll
+        for (int q = 1; q < 4; ++q) { goh[q] = goh[0]; gow[q] = gow[0]; }
+    }
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(smem_u32(&ctl->full[s]), 1);
+            mbar_init(smem_u32(&ctl->empty[s]), 1);
+        }
+        mbar_init(smem_u32(&ctl->accum), 1);
+        fence_barrier_init();
+    }
+    const uint32_t tmem_cols = two ? 128u : 64u;
+    if (warp == 4) tmem_alloc(smem_u32(&ctl->tmem_base), tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = ctl->tmem_base;
+
+    if (warp == 5) {
+        // ======================= TMA producer ===================================
+        if (lane == 0) {
+            int it = 0;
+            for (int ipix = 0; ipix < g.HW; ++ipix) {
+                const int ih = ipix / g.W, iw = ipix - ih * g.W;
+                int tap[4], any = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { tap[q] = (q < groups) ? tap_of(g, goh[q], gow[q], ih, iw) : -1; any |= (tap[q] >= 0); }
+                if (!any) continue;
+                for (int kb = 0; kb < p.n_kblk; ++kb, ++it) {
+                    const int s = it % stages;
+                    const uint32_t ph = (uint32_t)(it / stages) & 1u;
+                    mbar_wait(smem_u32(&ctl->empty[s]), ph ^ 1u);
+                    const uint32_t bar = smem_u32(&ctl->full[s]);
+                    uint32_t bytes = (uint32_t)planes * TC_A_BYTES;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) if (tap[q] >= 0) bytes += sub_bytes;
+                    mbar_arrive_expect_tx(bar, bytes);
+                    const uint32_t st = base + tiles_off + (uint32_t)s * stage_bytes;
+                    const int col = ipix * g.Cin + kb * 64;
+                    tma_load_2d(st + a_off, &tm_a, col, m0, bar);
+                    if (two) tma_load_2d(st + a2_off, &tm_a2, col, m0, bar);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (tap[q] < 0) continue;
+                        const __nv_bfloat16* src = p.wtiles + ((size_t)(tap[q] * p.n_cblk + cb) * p.n_kblk + kb) * ((size_t)planes * ng * 64);
+                        bulk_g2s(st + b_off + q * sub_bytes, src, sub_bytes, bar);
+                    }
+                }
+            }
+        }
+    } else if (warp == 4) {
+        // ======================= MMA issuer =====================================
+        const uint32_t idesc = make_idesc_bf16(TC_BM, ng);
+        uint32_t started = 0;
+        int it = 0;
+        for (int ipix = 0; ipix < g.HW; ++ipix) {
+            const int ih = ipix / g.W, iw = ipix - ih * g.W;
+            int tap[4], any = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { tap[q] = (q < groups) ? tap_of(g, goh[q], gow[q], ih, iw) : -1; any |= (tap[q] >= 0); }
+            if (!any) continue;
+            for (int kb = 0; kb < p.n_kblk; ++kb, ++it) {
+                const int s = it % stages;
+                const uint32_t ph = (uint32_t)(it / stages) & 1u;
+                mbar_wait(smem_u32(&ctl->full[s]), ph);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t st = base + tiles_off + (uint32_t)s * stage_bytes;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (tap[q] < 0) continue;
+                        const uint32_t acc0 = (started >> q) & 1u;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint64_t da = make_smem_desc_sw128(st + a_off + j * 32);
+                            const uint64_t db = make_smem_desc(st + b_off + q * sub_bytes + j * 2 * (ng * 16), ng * 16, 128);
+                            umma_bf16(tmem + q * ng, da, db, idesc, (acc0 | j) ? 1u : 0u);
+                            if (two) {
+                                const uint64_t da2 = make_smem_desc_sw128(st + a2_off + j * 32);
+                                const uint64_t db2 = make_smem_desc(st + b_off + q * sub_bytes + ng * 128 + j * 2 * (ng * 16), ng * 16, 128);
+                                umma_bf16(tmem + 64u + q * ng, da2, db2, idesc, (acc0 | j) ? 1u : 0u);
+                            }
+                        }
+                        started |= 1u << q;
+                    }
+                    umma_commit(smem_u32(&ctl->empty[s]));
+                }
+                __syncwarp();
+            }
+        }
+        if (lane == 0) umma_commit(smem_u32(&ctl->accum));
+        __syncwarp();
+        tc_fence_before();
+    } else {
+        // ======================= epilogue =======================================
+        const int t = threadIdx.x, b = m0 + t;
+        const bool bvalid = b < g.B;
+        mbar_wait(smem_u32(&ctl->accum), 0u);
+        tc_fence_after();
+        uint32_t started = 0;          // which column groups received at least one MMA (same schedule as warp 4)
+        for (int ipix = 0; ipix < g.HW; ++ipix) {
+            const int ih = ipix / g.W, iw = ipix - ih * g.W;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (q < groups && tap_of(g, goh[q], gow[q], ih, iw) >= 0) started |= 1u << q;
+        }
+        const NoiseKey nkey = effective_key(p.key, p.stream_base);
+        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+        const int npad = p.n_cblk * ng;
+        const bool stoch_lrt = two;
+        if (p.pool) {
+            // four column groups = the four pixels of one 2x2 window, 16 couts each
+            float best[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) best[j] = -INFINITY;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float am[16], av[16];
+                tmem_ld16(lane_base + (uint32_t)(q * 16), am);
+                if (two) tmem_ld16(lane_base + 64u + (uint32_t)(q * 16), av);
+                const bool live = (started >> q) & 1u;
+                const int pix = goh[q] * g.OW + gow[q];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int n = cb * 16 + j;
+                    float val = (live ? am[j] : 0.0f) + p.bias_ws[n];
+                    if (stoch_lrt && bvalid && n < g.N) {
+                        const size_t o = ((size_t)b * g.N + n) * g.OHW + pix;
+                        const float var = 1e-16f + ((live ? av[j] : 0.0f) + p.bias_ws[npad + n]);
+                        const float e_ = p.eps_a ? __ldg(p.eps_a + o) : normal1(o, nkey);
+                        val = val + sqrtf(var) * e_;
+                    }
+                    best[j] = fmaxf(best[j], val);
+                }
+            }
+            if (bvalid) {
+                float r[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) r[j] = apply_act(best[j], p.act);      // act is monotone: act(max) == max(act)
+                const int n0 = cb * 16;
+                if (p.out_mode == OUT_PACKED_BF16 && n0 + 16 <= g.N) {
+                    __nv_bfloat16* yo = reinterpret_cast<__nv_bfloat16*>(p.y) + (size_t)b * p.out_pitch + (size_t)pset * g.N + n0;
+                    uint4 v0 = make_uint4(pack_bf16(r[0], r[1]), pack_bf16(r[2], r[3]), pack_bf16(r[4], r[5]), pack_bf16(r[6], r[7]));
+                    uint4 v1 = make_uint4(pack_bf16(r[8], r[9]), pack_bf16(r[10], r[11]), pack_bf16(r[12], r[13]), pack_bf16(r[14], r[15]));
+                    reinterpret_cast<uint4*>(yo)[0] = v0; reinterpret_cast<uint4*>(yo)[1] = v1;
+                    if (p.y_sq) {
+                        __nv_bfloat16* ys = reinterpret_cast<__nv_bfloat16*>(p.y_sq) + (size_t)b * p.out_pitch + (size_t)pset * g.N + n0;
+                        uint4 s0 = make_uint4(pack_bf16(r[0] * r[0], r[1] * r[1]), pack_bf16(r[2] * r[2], r[3] * r[3]), pack_bf16(r[4] * r[4], r[5] * r[5]), pack_bf16(r[6] * r[6], r[7] * r[7]));
+                        uint4 s1 = make_uint4(pack_bf16(r[8] * r[8], r[9] * r[9]), pack_bf16(r[10] * r[10], r[11] * r[11]), pack_bf16(r[12] * r[12], r[13] * r[13]), pack_bf16(r[14] * r[14], r[15] * r[15]));
+                        reinterpret_cast<uint4*>(ys)[0] = s0; reinterpret_cast<uint4*>(ys)[1] = s1;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int n = n0 + j;
+                        if (n >= g.N) continue;
+                        if (p.out_mode == OUT_PACKED_BF16) {
+                            const size_t o = (size_t)b * p.out_pitch + (size_t)pset * g.N + n;
+                            reinterpret_cast<__nv_bfloat16*>(p.y)[o] = __float2bfloat16_rn(r[j]);
+                            if (p.y_sq) reinterpret_cast<__nv_bfloat16*>(p.y_sq)[o] = __float2bfloat16_rn(r[j] * r[j]);
+                        } else if (p.out_mode == OUT_ROWMAJOR_F32) {
+                            reinterpret_cast<float*>(p.y)[((size_t)b * (g.OHW >> 2) + pset) * g.N + n] = r[j];
+                        } else {   // NCHW fp32, pooled map
+                            reinterpret_cast<float*>(p.y)[((size_t)b * g.N + n) * (g.OHW >> 2) + pset] = r[j];
+                        }
+                    }
+                }
+            }
+        } else {
+            const bool live = started & 1u;
+            const int pix = pset;
+#pragma unroll 1
+            for (int c0 = 0; c0 < 64; c0 += 16) {
+                float am[16], av[16];
+                tmem_ld16(lane_base + (uint32_t)c0, am);
+                if (two) tmem_ld16(lane_base + 64u + (uint32_t)c0, av);
+                if (!bvalid) continue;
+                float r[16];
+                const int n0 = cb * 64 + c0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int n = n0 + j;
+                    float val = (live ? am[j] : 0.0f) + p.bias_ws[n];
+                    if (stoch_lrt && n < g.N) {
+                        const size_t o = ((size_t)b * g.N + n) * g.OHW + pix;
+                        const float var = 1e-16f + ((live ? av[j] : 0.0f) + p.bias_ws[npad + n]);
+                        const float e_ = p.eps_a ? __ldg(p.eps_a + o) : normal1(o, nkey);
+                        val = val + sqrtf(var) * e_;
+                    }
+                    r[j] = apply_act(val, p.act);
+                }
+                if (p.out_mode == OUT_PACKED_BF16 && n0 + 16 <= g.N) {
+                    __nv_bfloat16* yo = reinterpret_cast<__nv_bfloat16*>(p.y) + (size_t)b * p.out_pitch + (size_t)pix * g.N + n0;
+                    uint4 v0 = make_uint4(pack_bf16(r[0], r[1]), pack_bf16(r[2], r[3]), pack_bf16(r[4], r[5]), pack_bf16(r[6], r[7]));
+                    uint4 v1 = make_uint4(pack_bf16(r[8], r[9]), pack_bf16(r[10], r[11]), pack_bf16(r[12], r[13]), pack_bf16(r[14], r[15]));
+                    reinterpret_cast<uint4*>(yo)[0] = v0; reinterpret_cast<uint4*>(yo)[1] = v1;
+                    if (p.y_sq) {
+                        __nv_bfloat16* ys = reinterpret_cast<__nv_bfloat16*>(p.y_sq) + (size_t)b * p.out_pitch + (size_t)pix * g.N + n0;
+                        uint4 s0 = make_uint4(pack_bf16(r[0] * r[0], r[1] * r[1]), pack_bf16(r[2] * r[2], r[3] * r[3]), pack_bf16(r[4] * r[4], r[5] * r[5]), pack_bf16(r[6] * r[6], r[7] * r[7]));
+                        uint4 s1 = make_uint4(pack_bf16(r[8] * r[8], r[9] * r[9]), pack_bf16(r[10] * r[10], r[11] * r[11]), pack_bf16(r[12] * r[12], r[13] * r[13]), pack_bf16(r[14] * r[14], r[15] * r[15]));
+                        reinterpret_cast<uint4*>(ys)[0] = s0; reinterpret_cast<uint4*>(ys)[1] = s1;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int n = n0 + j;
+                        if (n >= g.N) continue;
+                        if (p.out_mode == OUT_PACKED_BF16) {
+                            const size_t o = (size_t)b * p.out_pitch + (size_t)pix * g.N + n;
+                            reinterpret_cast<__nv_bfloat16*>(p.y)[o] = __float2bfloat16_rn(r[j]);
+                            if (p.y_sq) reinterpret_cast<__nv_bfloat16*>(p.y_sq)[o] = __float2bfloat16_rn(r[j] * r[j]);
+                        } else if (p.out_mode == OUT_ROWMAJOR_F32) {
+                            reinterpret_cast<float*>(p.y)[((size_t)b * g.OHW + pix) * g.N + n] = r[j];
+                        } else {
+                            reinterpret_cast<float*>(p.y)[((size_t)b * g.N + n) * g.OHW + pix] = r[j];
+                        }
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 4) tmem_dealloc(tmem, tmem_cols);
+}
+
+// ------------------------------------------------------------- host side
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline PFN_tmapEncodeTiled tmap_encoder() {
+    static PFN_tmapEncodeTiled fn = nullptr;
+    if (!fn) {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_tmapEncodeTiled)f;
+    }
+    return fn;
+}
+// packed bf16 activation [rows, cols] with row pitch `pitch` elements -> box [64 cols x 128 rows], 128B swizzle
+inline bool make_act_tmap(CUtensorMap* tm, const void* ptr, int rows, int cols, int pitch) {
+    PFN_tmapEncodeTiled enc = tmap_encoder();
+    if (!enc) return false;
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)pitch * 2};
+    cuuint32_t box[2] = {64, 128};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+inline bool fused_supported(const Geom& g, int pool) {
+    if (g.DH != 1 || g.DW != 1) return false;
+    if (g.HW > 64) return false;                       // "small map" regime
+    if (pool && ((g.OH & 1) || (g.OW & 1))) return false;
+    if (g.Cin % 8) return false;                       // TMA: 16-byte aligned column offsets per pixel
+    return true;
+}
+
+inline cudaError_t launch_fused(FusedArgs a, const void* x, const void* x_sq, cudaStream_t st, int* n_launch, const char** why) {
+    const Geom& g = a.g;
+    *n_launch = 0;
+    a.planes = tc_planes(a.variant, a.sample);
+    a.ng = a.pool ? 16 : 64;
+    a.n_cblk = (g.N + a.ng - 1) / a.ng;
+    a.n_kblk = (g.Cin + 63) / 64;
+    a.taps = g.KHW;
+    const bool lrt = a.variant == BBB_VARIANT_LRT;
+    CUtensorMap tma, tma2;
+    if (!make_act_tmap(&tma, x, g.B, g.HW * g.Cin, a.in_pitch)) { *why = "cuTensorMapEncodeTiled failed (A)"; return cudaErrorInvalidValue; }
+    if (a.planes == 2) {
+        if (!x_sq) { *why = "LRT fused layer needs the squared activation"; return cudaErrorInvalidValue; }
+        if (!make_act_tmap(&tma2, x_sq, g.B, g.HW * g.Cin, a.in_pitch)) { *why = "cuTensorMapEncodeTiled failed (A^2)"; return cudaErrorInvalidValue; }
+    } else tma2 = tma;
+    {
+        int grid = a.n_cblk * a.n_kblk;
+        if (grid > 2048) grid = 2048;
+        if (lrt) tap_prep_kernel<BBB_VARIANT_LRT><<<grid, 256, 0, st>>>(a);
+        else     tap_prep_kernel<BBB_VARIANT_BBB><<<grid, 256, 0, st>>>(a);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        *n_launch += 1;
+    }
+    const int stages = 4;                                            // 96 KB (1 plane) / 192 KB (2 planes)
+    const size_t smem = 2048 + (size_t)stages * tc_stage_bytes(a.planes);
+    const int psets = a.pool ? (g.OH / 2) * (g.OW / 2) : g.OHW;
+    dim3 grid(psets * a.n_cblk, (g.B + TC_BM - 1) / TC_BM);
+    cudaError_t e;
+    if (lrt) {
+        e = cudaFuncSetAttribute(tap_gemm_kernel<BBB_VARIANT_LRT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        tap_gemm_kernel<BBB_VARIANT_LRT><<<grid, 192, smem, st>>>(a, tma, tma2, stages);
+    } else {
+        e = cudaFuncSetAttribute(tap_gemm_kernel<BBB_VARIANT_BBB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        tap_gemm_kernel<BBB_VARIANT_BBB><<<grid, 192, smem, st>>>(a, tma, tma2, stages);
+    }
+    e = cudaGetLastError();
+    if (e == cudaSuccess) *n_launch += 1;
+    return e;
+}
+
+}  // namespace bbb

@@ -47,6 +47,8 @@ struct TcArgs {
     float* bias_ws;          // [2][Npad]: row 0 = bias (BBB: sampled; LRT: mu), row 1 = LRT sigma_b^2
     int n_tiles, k_blocks, planes;
     int skip_prep;
+    // fused epilogue (first layer of a fused chain): 2x2 max-pool + packed bf16 output
+    void* y_sq; int out_mode, out_pitch, pool;     // out_mode: 0 packed bf16 [B,(pix,c)], 2 NCHW fp32 (default)
 };
 
 constexpr int TC_BM = 128, TC_BN = 64, TC_BK = 64;
@@ -294,9 +296,16 @@ gemm_tc_kernel(const TcArgs p, const int stages) {
         const bool mvalid = m < g.M;
         int ih0 = 0, iw0 = 0; long xb = 0;
         int bimg = 0, pix = 0;
+        int pwin = 0;                                  // pooled-window index (pool mode)
         if (mvalid) {
             bimg = m / g.OHW; pix = m - bimg * g.OHW;
-            const int oh = pix / g.OW, ow = pix - oh * g.OW;
+            int oh, ow;
+            if (p.pool) {                               // rows ordered (image, window, 2x2 position): a quad of lanes == one pool window
+                pwin = pix >> 2;
+                const int wy = pwin / (g.OW >> 1), wx = pwin - wy * (g.OW >> 1);
+                oh = 2 * wy + ((pix >> 1) & 1); ow = 2 * wx + (pix & 1);
+                pix = oh * g.OW + ow;
+            } else { oh = pix / g.OW; ow = pix - oh * g.OW; }
             ih0 = oh * g.SH - g.PH; iw0 = ow * g.SW - g.PW;
             xb = (long)bimg * g.Cin * g.HW + (long)ih0 * g.W + iw0;
         }
@@ -337,26 +346,56 @@ gemm_tc_kernel(const TcArgs p, const int stages) {
         const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
         const int npad = p.n_tiles * TC_BN;
         float* __restrict__ y = reinterpret_cast<float*>(p.y);
+        const int ohw_out = p.pool ? (g.OHW >> 2) : g.OHW;
+        const int opix = p.pool ? pwin : pix;
 #pragma unroll 1
         for (int c0 = 0; c0 < TC_BN; c0 += 16) {
-            float am[16], av[16];
+            float am[16], av[16], r[16];
             tmem_ld16(lane_base + (uint32_t)c0, am);
             if (two) tmem_ld16(lane_base + 64u + (uint32_t)c0, av);
-            if (mvalid) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int n = n0 + c0 + j;
+                float val = -INFINITY;
+                if (mvalid && n < g.N) {
+                    const size_t o = ((size_t)bimg * g.N + n) * g.OHW + pix;
+                    val = am[j] + p.bias_ws[n];
+                    if (two) {
+                        const float var = 1e-16f + (av[j] + p.bias_ws[npad + n]);
+                        const float sd = sqrtf(var);
+                        const float e_ = p.eps_a ? __ldg(p.eps_a + o) : normal1(o, nkey);
+                        val = val + sd * e_;
+                        if (p.act_std) p.act_std[o] = sd;
+                    }
+                }
+                if (p.pool) {                           // 2x2 max-pool across the lane quad
+                    val = fmaxf(val, __shfl_xor_sync(0xffffffffu, val, 1));
+                    val = fmaxf(val, __shfl_xor_sync(0xffffffffu, val, 2));
+                }
+                r[j] = apply_act(val, p.act);
+            }
+            if (!mvalid || (p.pool && (threadIdx.x & 3))) continue;
+            const int nb = n0 + c0;
+            if (p.out_mode == 0 && nb + 16 <= g.N) {
+                __nv_bfloat16* yo = reinterpret_cast<__nv_bfloat16*>(p.y) + (size_t)bimg * p.out_pitch + (size_t)opix * g.N + nb;
+                reinterpret_cast<uint4*>(yo)[0] = make_uint4(pack_bf16(r[0], r[1]), pack_bf16(r[2], r[3]), pack_bf16(r[4], r[5]), pack_bf16(r[6], r[7]));
+                reinterpret_cast<uint4*>(yo)[1] = make_uint4(pack_bf16(r[8], r[9]), pack_bf16(r[10], r[11]), pack_bf16(r[12], r[13]), pack_bf16(r[14], r[15]));
+                if (p.y_sq) {
+                    __nv_bfloat16* ys = reinterpret_cast<__nv_bfloat16*>(p.y_sq) + (size_t)bimg * p.out_pitch + (size_t)opix * g.N + nb;
+                    reinterpret_cast<uint4*>(ys)[0] = make_uint4(pack_bf16(r[0] * r[0], r[1] * r[1]), pack_bf16(r[2] * r[2], r[3] * r[3]), pack_bf16(r[4] * r[4], r[5] * r[5]), pack_bf16(r[6] * r[6], r[7] * r[7]));
+                    reinterpret_cast<uint4*>(ys)[1] = make_uint4(pack_bf16(r[8] * r[8], r[9] * r[9]), pack_bf16(r[10] * r[10], r[11] * r[11]), pack_bf16(r[12] * r[12], r[13] * r[13]), pack_bf16(r[14] * r[14], r[15] * r[15]));
+                }
+            } else {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const int n = n0 + c0 + j;
-                    if (n < g.N) {
-                        const size_t o = ((size_t)bimg * g.N + n) * g.OHW + pix;
-                        float val = am[j] + p.bias_ws[n];
-                        if (two) {
-                            const float var = 1e-16f + (av[j] + p.bias_ws[npad + n]);
-                            const float sd = sqrtf(var);
-                            const float e_ = p.eps_a ? __ldg(p.eps_a + o) : normal1(o, nkey);
-                            val = val + sd * e_;
-                            if (p.act_std) p.act_std[o] = sd;
-                        }
-                        y[o] = apply_act(val, p.act);
+                    const int n = nb + j;
+                    if (n >= g.N) continue;
+                    if (p.out_mode == 0) {
+                        const size_t o = (size_t)bimg * p.out_pitch + (size_t)opix * g.N + n;
+                        reinterpret_cast<__nv_bfloat16*>(p.y)[o] = __float2bfloat16_rn(r[j]);
+                        if (p.y_sq) reinterpret_cast<__nv_bfloat16*>(p.y_sq)[o] = __float2bfloat16_rn(r[j] * r[j]);
+                    } else {
+                        y[((size_t)bimg * g.N + n) * ohw_out + opix] = r[j];
                     }
                 }
             }

@@ -1,0 +1,176 @@
+"""Fused execution of a ModuleWrapper's children.
+
+The reference's model files interleave the Bayesian layers with ``nn.Softplus`` /
+``nn.ReLU``, ``nn.MaxPool2d(2, 2)`` and ``FlattenLayer`` children
+(BayesianAlexNet.py:34-53).  ``ModuleWrapper.forward`` (layers/misc.py:16-18) just
+calls them in order; here the same child list is pattern-matched into runs of
+``[Bayesian layer, activation?, 2x2 max-pool?, flatten*]`` and each run becomes ONE
+``bbb_layer_forward_fused`` call (weight-prep kernel + tcgen05 GEMM kernel whose
+epilogue applies the activation and the pool and writes the packed bf16 format the
+next layer's TMA loads).  The model files stay unmodified; anything that does not
+match (other pools, other modules, autograd needed) falls back to the plain
+child-by-child path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+from torch import nn
+
+from . import _lib as L
+from . import functional as Fn
+
+
+class _Step:
+    __slots__ = ("layer", "act", "pool", "conv", "in_shape", "in_layout", "prev_hw", "out_layout", "out_chw",
+                 "eps_shape", "linear")
+
+
+def _act_code(m):
+    if isinstance(m, nn.Softplus) and m.beta == 1 and m.threshold == 20:
+        return L.ACT_SOFTPLUS
+    if isinstance(m, nn.ReLU):
+        return L.ACT_RELU
+    return None
+
+
+def _is_pool22(m):
+    def two(v):
+        return v == 2 or v == (2, 2)
+    return (isinstance(m, nn.MaxPool2d) and two(m.kernel_size) and two(m.stride) and m.padding in (0, (0, 0))
+            and m.dilation in (1, (1, 1)) and not m.ceil_mode and not m.return_indices)
+
+
+def plan(children, x_shape):
+    """Return the list of fused steps for this child list and input shape, or None."""
+    from .modules import _BayesLayer, FlattenLayer
+    if len(x_shape) != 4:
+        return None
+    _, c, h, w = x_shape
+    state = ("nchw", c, h, w)
+    steps = []
+    i, n = 0, len(children)
+    while i < n:
+        m = children[i]
+        if not isinstance(m, _BayesLayer) or m.math not in ("bf16", "auto"):
+            return None
+        st = _Step()
+        st.layer = m
+        st.conv = m._conv_geometry()
+        st.linear = st.conv is None
+        lay, c, h, w = state
+        if st.linear:
+            if lay != "packed" or m.in_features != c * h * w:
+                return None
+            st.prev_hw = h * w
+            st.in_shape = (c * h * w, 1, 1)
+            cout, oh, ow = m.out_features, 1, 1
+        else:
+            if m.in_channels != c:
+                return None
+            (sh, sw), (ph, pw), (dh, dw) = st.conv
+            if (dh, dw) != (1, 1):
+                return None
+            kh, kw = m.kernel_size
+            oh, ow = (h + 2 * ph - kh) // sh + 1, (w + 2 * pw - kw) // sw + 1
+            if oh < 1 or ow < 1:
+                return None
+            if lay == "packed" and (h * w > 64 or c % 8):
+                return None
+            st.prev_hw = 1
+            st.in_shape = (c, h, w)
+            cout = m.out_channels
+        st.in_layout = L.LAYOUT_NCHW_F32 if lay == "nchw" else L.LAYOUT_PACKED_BF16
+        st.eps_shape = (cout, oh, ow)
+        i += 1
+        st.act = L.ACT_NONE
+        if i < n and _act_code(children[i]) is not None:
+            st.act = _act_code(children[i])
+            i += 1
+        st.pool = False
+        if i < n and isinstance(children[i], nn.MaxPool2d):
+            if not _is_pool22(children[i]) or st.linear or oh % 2 or ow % 2:
+                return None
+            st.pool = True
+            oh, ow = oh // 2, ow // 2
+            i += 1
+        while i < n and isinstance(children[i], FlattenLayer):
+            if children[i].num_features != cout * oh * ow:
+                return None            # the reference's view(-1, F) would fold the batch: not fused
+            i += 1
+        st.out_chw = (cout, oh, ow)
+        state = ("packed", cout, oh, ow)
+        steps.append(st)
+    if not steps:
+        return None
+    last = steps[-1]
+    last.out_layout = L.LAYOUT_ROWMAJOR_F32 if last.out_chw[1] * last.out_chw[2] == 1 else L.LAYOUT_NCHW_F32
+    for st in steps[:-1]:
+        st.out_layout = L.LAYOUT_PACKED_BF16
+    return steps
+
+
+def run(steps, x: torch.Tensor):
+    """Execute a planned chain.  Returns the network output (fp32)."""
+    lib = L.lib()
+    dev = x.device
+    B = x.shape[0]
+    cur, cur_sq, cur_pitch = x.contiguous().float(), None, 0
+    for st in steps:
+        m = st.layer
+        lrt = m._variant == L.VARIANT_LRT
+        stoch = True                                     # ModuleWrapper calls children with sample=True
+        cin, h, w = st.in_shape
+        d = L.LayerDesc()
+        d.batch, d.in_channels, d.in_h, d.in_w = B, cin, h, w
+        if st.linear:
+            d.out_channels, d.kernel_h, d.kernel_w = m.out_features, 1, 1
+            d.stride_h = d.stride_w = d.dil_h = d.dil_w = 1
+            d.pad_h = d.pad_w = 0
+        else:
+            (sh, sw), (ph, pw), (dh, dw) = st.conv
+            d.out_channels, d.kernel_h, d.kernel_w = m.out_channels, m.kernel_size[0], m.kernel_size[1]
+            d.stride_h, d.stride_w, d.pad_h, d.pad_w, d.dil_h, d.dil_w = sh, sw, ph, pw, dh, dw
+        d.variant, d.sample, d.has_bias = m._variant, 1, int(m.use_bias)
+        d.act_dtype, d.math = L.DTYPE_F32, L.MATH_BF16_TC
+        d.kl_convention = L.KL_BY_NAME[m.kl_convention]
+        d.epilogue_act = st.act
+        d.pool_k = d.pool_s = 2 if st.pool else 0
+        d.prior_mu, d.prior_sigma = float(m.prior_mu), float(m.prior_sigma)
+        cout, oh, ow = st.out_chw
+        if st.out_layout == L.LAYOUT_PACKED_BF16:
+            pitch = (cout * oh * ow + 7) // 8 * 8
+            y = torch.empty(B, pitch, dtype=torch.bfloat16, device=dev)
+            nxt = steps[steps.index(st) + 1].layer
+            y_sq = torch.empty_like(y) if nxt._variant == L.VARIANT_LRT else None
+        elif st.out_layout == L.LAYOUT_ROWMAJOR_F32:
+            pitch, y, y_sq = 0, torch.empty(B, cout, dtype=torch.float32, device=dev), None
+        else:
+            pitch, y, y_sq = 0, torch.empty(B, cout, oh, ow, dtype=torch.float32, device=dev), None
+        kl = torch.empty((), dtype=torch.float32, device=dev)
+        eps_a = eps_b = None
+        seed = stream_id = 0
+        base = None
+        if stoch:
+            if Fn.external_eps_active():
+                if lrt:
+                    eps_a = Fn._pop_eps((B,) + st.eps_shape if not st.linear else (B, st.eps_shape[0]), dev)
+                else:
+                    eps_a = Fn._pop_eps(m.W_mu.shape, dev)
+                    if m.use_bias:
+                        eps_b = Fn._pop_eps(m.bias_mu.shape, dev)
+            else:
+                seed, stream_id = Fn.next_stream()
+                base = Fn._noise.base
+        ws = Fn.workspace(dev, d, id(m))
+        rc = lib.bbb_layer_forward_fused(
+            C.byref(d), Fn._ptr(cur), Fn._ptr(cur_sq), st.in_layout, cur_pitch, st.prev_hw,
+            Fn._ptr(m.W_mu), Fn._ptr(m.W_rho), Fn._ptr(m.bias_mu), Fn._ptr(m.bias_rho),
+            Fn._ptr(y), Fn._ptr(y_sq), st.out_layout, pitch, Fn._ptr(kl), Fn._ptr(eps_a), Fn._ptr(eps_b),
+            C.c_uint64(seed), C.c_uint64(stream_id), Fn._ptr(base), Fn._ptr(ws), C.c_size_t(ws.numel()),
+            Fn._stream(dev))
+        L.check(rc, "bbb_layer_forward_fused")
+        m._kl_cache = (kl, m._versions(), torch.is_grad_enabled())
+        cur, cur_sq, cur_pitch = y, y_sq, pitch
+    return cur

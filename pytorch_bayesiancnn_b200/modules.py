@@ -35,6 +35,10 @@ def _default_math() -> str:
     return os.environ.get("BBB_B200_MATH", "fp32")
 
 
+def _default_fuse() -> bool:
+    return os.environ.get("BBB_B200_FUSE", "1") != "0"
+
+
 class ModuleWrapper(nn.Module):
     """layers/misc.py:4-25: universal forward returning (x, kl); recursive set_flag."""
 
@@ -47,9 +51,36 @@ class ModuleWrapper(nn.Module):
             if hasattr(child, "set_flag"):
                 child.set_flag(flag_name, value)
 
+    def _try_fused(self, x):
+        """Run the children as a fused tcgen05 chain if they match (see fused.py); None = not fusable."""
+        if not (torch.is_tensor(x) and x.is_cuda and x.dim() == 4) or not getattr(self, "fuse", _default_fuse()):
+            return None
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            return None                                    # the fused chain is forward-only
+        from . import fused
+        plans = self.__dict__.setdefault("_fused_plans", {})
+        key = tuple(x.shape[1:])
+        if key not in plans:
+            kids = list(self.children())
+            plans[key] = fused.plan(kids, tuple(x.shape)) if kids else None
+        steps = plans[key]
+        if steps is None:
+            return None
+        try:
+            return fused.run(steps, x)
+        except L.EngineError as e:
+            if "code -2" not in str(e):                    # anything but BBB_E_UNSUPPORTED is a real error
+                raise
+            plans[key] = None
+            return None
+
     def forward(self, x):
-        for child in self.children():
-            x = child(x)
+        out = self._try_fused(x)
+        if out is not None:
+            x = out
+        else:
+            for child in self.children():
+                x = child(x)
         kl = 0.0
         for m in self.modules():
             if hasattr(m, "kl_loss"):

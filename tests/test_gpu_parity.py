@@ -319,3 +319,52 @@ def test_tc_philox_equals_external_draw(dev):
         with torch.no_grad(), bbb.external_eps(eps):
             y2 = layer(x)
         assert scale_err(y1, y2) < 1e-6
+
+
+# --------------------------------------------------------------------------- #
+# fused chain (activation + pool in the epilogue, packed bf16 between layers)
+# --------------------------------------------------------------------------- #
+def _alexnet(variant, classes, dev, act="softplus"):
+    from pytorch_bayesiancnn_b200 import models as M
+    from oracle import bbb_oracle as O
+    params = O.init_params("alexnet", classes, 3, CFG_PRIORS, seed=123)
+    net = load_params_into(M.BBBAlexNet(classes, 3, CFG_PRIORS, variant, act), params).to(dev).train()
+    net.set_flag("math", "bf16")
+    return net, params
+
+
+def test_fused_chain_vs_oracle_external_eps(dev):
+    """Whole BBBAlexNet through the fused tcgen05 chain vs the oracle on identical eps,
+    at a batch that is not a multiple of the 128-row tile and at the BASELINE batch."""
+    import pytorch_bayesiancnn_b200 as bbb
+    from oracle import bbb_oracle as O
+    for variant in ("lrt", "bbb"):
+        for (batch, classes, act) in ((37, 10, "softplus"), (512, 10, "softplus"), (130, 100, "relu")):
+            net, params = _alexnet(variant, classes, dev, act)
+            assert net._try_fused is not None
+            x = torch.randn(batch, 3, 32, 32, generator=torch.Generator().manual_seed(1))
+            eps = O.draw_eps_like_reference(O.eps_shapes("alexnet", classes, 3, variant, batch), seed=9)
+            ref, refkl = O.net_forward("alexnet", params, x, eps, variant, act, 0.0, 0.1, classes)
+            with torch.no_grad(), bbb.external_eps(eps):
+                logits, kl = net(x.to(dev))
+            assert net._fused_plans[(3, 32, 32)] is not None          # it really took the fused path
+            e = scale_err(logits, ref)
+            print("fused", variant, batch, classes, act, "scale err", e)
+            assert e < 2 * BF16_TOL, (variant, batch, e)
+            assert abs(float(kl) - float(refkl)) <= KL_TOL * abs(float(refkl))
+
+
+def test_fused_equals_unfused_same_philox(dev):
+    import pytorch_bayesiancnn_b200 as bbb
+    for variant in ("lrt", "bbb"):
+        net, _ = _alexnet(variant, 10, dev)
+        x = torch.randn(256, 3, 32, 32, device=dev)
+        with torch.no_grad():
+            bbb.manual_seed(3); a, kla = net(x)
+            net.set_flag("fuse", False)
+            bbb.manual_seed(3); b, klb = net(x)
+            net.set_flag("fuse", True)
+            bbb.manual_seed(3); c, _ = net(x)
+        assert torch.equal(a, c)
+        assert scale_err(a, b) < BF16_TOL, (variant, scale_err(a, b))   # same noise, bf16 inter-layer rounding only
+        assert float(kla) == float(klb)

@@ -113,3 +113,27 @@ def test_product_never_imports_oracle():
                 assert "oracle" not in src.replace("# checker", ""), f
     for f in ("layers/__init__.py",):
         assert "oracle" not in open(os.path.join(ROOT, f)).read()
+
+
+def test_fused_planner_matches_reference_child_lists():
+    """fused.plan() pattern-matches the (unmodified) child list of the model files."""
+    from pytorch_bayesiancnn_b200 import fused, _lib as L
+    from pytorch_bayesiancnn_b200.models import BBBAlexNet, BBBLeNet, BBB3Conv3FC
+    for variant in ("lrt", "bbb"):
+        net = BBBAlexNet(10, 3, CFG_PRIORS, variant, "softplus")
+        net.set_flag("math", "bf16")
+        steps = fused.plan(list(net.children()), (512, 3, 32, 32))
+        assert steps is not None and len(steps) == 6
+        assert [s.pool for s in steps] == [True, True, False, False, True, False]
+        assert [s.act for s in steps] == [L.ACT_SOFTPLUS] * 5 + [L.ACT_NONE]
+        assert [s.out_chw for s in steps] == [(64, 4, 4), (192, 2, 2), (384, 2, 2), (256, 2, 2), (128, 1, 1), (10, 1, 1)]
+        assert steps[0].in_layout == L.LAYOUT_NCHW_F32 and all(s.in_layout == L.LAYOUT_PACKED_BF16 for s in steps[1:])
+        assert steps[-1].out_layout == L.LAYOUT_ROWMAJOR_F32 and steps[-1].linear and steps[-1].prev_hw == 1
+    # 3x3 stride-2 pools (Bayesian3Conv3FC.py:38) and 6-channel maps (LeNet) are not fusable -> plain path
+    n3 = BBB3Conv3FC(10, 1, CFG_PRIORS); n3.set_flag("math", "bf16")
+    assert fused.plan(list(n3.children()), (8, 1, 32, 32)) is None
+    nl = BBBLeNet(10, 3, CFG_PRIORS); nl.set_flag("math", "bf16")
+    assert fused.plan(list(nl.children()), (8, 3, 32, 32)) is None
+    # fp32 math is never fused
+    na = BBBAlexNet(10, 3, CFG_PRIORS)
+    assert fused.plan(list(na.children()), (8, 3, 32, 32)) is None
