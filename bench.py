@@ -288,29 +288,45 @@ def run_ours(args):
 
 
 def layer_rooflines(net, x, args, pk, flush, reps=20):
-    """Time each Bayesian layer's fused kernel alone (CUDA events on the launching
-    stream, L2 flushed between launches) and report algorithmic FLOP/s and B/s."""
+    """Time each Bayesian layer call alone: the call (prep + GEMM kernels; fused chain
+    step when the net runs fused) is captured in its own CUDA graph so host launch
+    overhead stays out, replayed with CUDA events on the launching stream, L2 flushed
+    (untimed) before every replay."""
     import pytorch_bayesiancnn_b200 as bbb
+    from pytorch_bayesiancnn_b200 import fused
     rows = layer_table(args.batch, args.classes)
-    acts = {}
-    h = x
+    steps = fused.plan(list(net.children()), tuple(x.shape)) if getattr(net, "fuse", True) else None
+    calls = []
     with torch.no_grad():
-        for name, m in net.named_children():
-            if hasattr(m, "W_mu"):
-                acts[name] = h
-            h = m(h)
+        if steps is not None:
+            cur, cur_sq, pitch = x.contiguous().float(), None, 0
+            for i, st in enumerate(steps):
+                nxt = steps[i + 1].layer if i + 1 < len(steps) else None
+                calls.append((lambda st=st, nxt=nxt, a=cur, b=cur_sq, c=pitch: fused.run_step(st, nxt, a, b, c)))
+                cur, cur_sq, pitch = fused.run_step(st, nxt, cur, cur_sq, pitch)
+        else:
+            h = x
+            for name, m in net.named_children():
+                if hasattr(m, "W_mu"):
+                    calls.append((lambda m=m, a=h.contiguous(): m(a)))
+                h = m(h)
     out = []
-    for row in rows:
-        m = getattr(net, row["name"])
-        xin = acts[row["name"]].contiguous()
-        times = []
+    for row, call in zip(rows, calls):
         with torch.no_grad():
-            for _ in range(3):
-                m(xin)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                call(); call()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                call()
+            times = []
             for _ in range(reps):
                 flush.zero_()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(); m(xin); e1.record()
+                e0.record(); gr.replay(); e1.record()
                 torch.cuda.synchronize()
                 times.append(e0.elapsed_time(e1))
         ms = statistics.median(times)
@@ -321,7 +337,7 @@ def layer_rooflines(net, x, args, pk, flush, reps=20):
         out.append({"name": row["name"], "gemm": [row["M"], row["N"], row["K"]], "ms": ms,
                     "gflop": fl / 1e9, "mbytes": by / 1e6, "bound": bound,
                     "tflops": fl / (ms * 1e-3) / 1e12, "gbs": by / (ms * 1e-3) / 1e9,
-                    "frac": max(t_tc, t_hbm) / (ms * 1e-3)})
+                    "frac": max(t_tc, t_hbm) / (ms * 1e-3), "fused": steps is not None})
     top = max(out, key=lambda r: r["ms"])
     if top["bound"] == "tensor":
         roof = {"kernel": top["name"], "bound": "tensor", "achieved": top["tflops"], "peak": pk["tf_burst"],

@@ -15,6 +15,7 @@ namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
+long long* g_trace = nullptr;      // debug hook (bbb_debug_set_trace)
 
 int fail(int code, const char* fmt, ...) {
     va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
@@ -227,7 +228,7 @@ int bbb_layer_forward_fused(const bbb_layer_desc* d, const void* x, const void* 
         a.wtiles = (__nv_bfloat16*)((char*)ws + kTcOffset);
         a.bias_ws = (float*)((char*)ws + kTcOffset + cpad * kpad * g.KHW * 4);
         a.prev_hw = prev_hw; a.y = y; a.y_sq = y_sq; a.out_mode = out_mode; a.out_pitch = out_pitch; a.pool = pool;
-        a.in_pitch = in_pitch;
+        a.in_pitch = in_pitch; a.trace = g_trace;
         const char* why = "";
         cudaError_t e = bbb::launch_fused(a, x, x_sq, st, &nl, &why);
         if (e != cudaSuccess) return fail(BBB_E_CUDA, "fused tap-GEMM launch: %s %s", cudaGetErrorString(e), why);
@@ -309,6 +310,9 @@ int bbb_noise_advance(uint64_t* base, uint64_t inc, void* cuda_stream) {
     g_launches += 1;
     return BBB_OK;
 }
+
+/* debug only (not in the public header): per-CTA clock64 checkpoints of tap_gemm_kernel */
+void bbb_debug_set_trace(void* dev_ptr) { g_trace = (long long*)dev_ptr; }
 
 const char* bbb_last_error(void) { return g_err; }
 int32_t bbb_abi_version(void) { return BBB_ABI_VERSION; }

@@ -81,8 +81,11 @@ __device__ __forceinline__ float4 normal4(uint64_t grp, const NoiseKey& k) {
     return z;
 }
 
-// the normal of one element (tiling independent: same value whoever asks)
-__device__ __forceinline__ float normal1(uint64_t idx, const NoiseKey& k) {
+// the normal of one element (tiling independent: same value whoever asks).
+// Deliberately NOT inlined: ~110 SASS instructions per copy, and the kernels that call it
+// are instruction-cache bound when it is replicated at every unrolled call site (ncu:
+// stall_no_instructions dominated the first tcgen05 kernels).
+__device__ __noinline__ float normal1(uint64_t idx, const NoiseKey k) {
     const uint4 r = philox4x32_10(make_uint4((uint32_t)(idx >> 2), (uint32_t)(idx >> 34), k.stream_lo, k.stream_hi),
                                   make_uint2(k.seed_lo, k.seed_hi));
     const uint32_t lane = (uint32_t)idx & 3u;
@@ -93,11 +96,11 @@ __device__ __forceinline__ float normal1(uint64_t idx, const NoiseKey& k) {
 
 // ------------------------------------------------------- elementwise math ----
 // sigma = log1p(exp(rho)) exactly as the reference writes it (no threshold).
-__device__ __forceinline__ float softplus_sigma(float rho) { return log1pf(expf(rho)); }
+__device__ __noinline__ float softplus_sigma(float rho) { return log1pf(expf(rho)); }
 
 // one KL term, reference convention: metrics.py:28 with (mu_q,sig_q) = prior and
 // (mu_p,sig_p) = posterior (the call-site binding); same op order.
-__device__ __forceinline__ float kl_term(float mu, float sigma, float pm, float ps, int convention) {
+__device__ __noinline__ float kl_term(float mu, float sigma, float pm, float ps, int convention) {
     if (convention == BBB_KL_REFERENCE) {
         const float a = 2.0f * logf(sigma / ps);
         const float b = ps / sigma;

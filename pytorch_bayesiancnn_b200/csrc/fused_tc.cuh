@@ -26,7 +26,6 @@
 
 namespace bbb {
 
-enum { OUT_PACKED_BF16 = 0, OUT_ROWMAJOR_F32 = 1, OUT_NCHW_F32 = 2 };
 
 struct FusedArgs {
     Geom g;
@@ -40,6 +39,7 @@ struct FusedArgs {
     int prev_hw;                 // linear fed by a flattened HxW map: k' = pix*C + c  <->  ref k = c*HW + pix
     void* y; void* y_sq;
     int out_mode, out_pitch, pool, in_pitch;
+    long long* trace;            // debug: per-CTA clock64 checkpoints (nullptr in production)
 };
 
 __host__ __device__ inline size_t fused_wtile_elems(const FusedArgs& a) { return (size_t)a.planes * a.ng * 64; }
@@ -58,48 +58,47 @@ tap_prep_kernel(const FusedArgs p) {
     const Geom& g = p.g;
     const NoiseKey nkey = effective_key(p.key, p.stream_base);
     const bool stoch = p.sample != 0, do_kl = p.kl_out != nullptr;
-    const int n_pairs = p.n_cblk * p.n_kblk;
     const int cprev = g.Cin / p.prev_hw;
     const size_t sub = fused_wtile_elems(p);
+    const int per_sub = p.ng * 8;                                  // (row, 8-wide K chunk) items per sub-tile
+    const long n_items = (long)p.taps * p.n_cblk * p.n_kblk * per_sub;
     double kl_acc = 0.0;
-    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-        const int cb = pair / p.n_kblk, kb = pair - cb * p.n_kblk;
-        for (int tap = 0; tap < p.taps; ++tap) {
-            __nv_bfloat16* dst = p.wtiles + ((size_t)(tap * p.n_cblk + cb) * p.n_kblk + kb) * sub;
-            for (int item = threadIdx.x; item < p.ng * 8; item += blockDim.x) {
-                const int row = item % p.ng, chunk = item / p.ng;
-                const int n = cb * p.ng + row;
-                float w[8], s2[8];
+    for (long gi = (long)blockIdx.x * blockDim.x + threadIdx.x; gi < n_items; gi += (long)gridDim.x * blockDim.x) {
+        const int st = (int)(gi / per_sub), item = (int)(gi - (long)st * per_sub);
+        const int kb = st % p.n_kblk, cb = (st / p.n_kblk) % p.n_cblk, tap = st / (p.n_kblk * p.n_cblk);
+        __nv_bfloat16* dst = p.wtiles + (size_t)st * sub;          // st == (tap*n_cblk + cb)*n_kblk + kb
+        const int row = item % p.ng, chunk = item / p.ng;
+        const int n = cb * p.ng + row;
+        float w[8], s2[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const int kq = kb * 64 + chunk * 8 + e;        // packed input-channel index
-                    float wv = 0.0f, sv = 0.0f;
-                    if (n < g.N && kq < g.Cin) {
-                        const int cin = (p.prev_hw > 1) ? ((kq % cprev) * p.prev_hw + kq / cprev) : kq;
-                        const size_t wi = (size_t)n * g.K + (size_t)cin * g.KHW + tap;
-                        const float mu = __ldg(p.w_mu + wi);
-                        float sigma = 0.0f;
-                        if (stoch || do_kl) sigma = softplus_sigma(__ldg(p.w_rho + wi));
-                        if (LRT) { wv = mu; sv = sigma * sigma; }
-                        else if (stoch) {
-                            const float e_ = p.eps_a ? __ldg(p.eps_a + wi) : normal1(wi, nkey);
-                            wv = mu + e_ * sigma;
-                        } else wv = mu;
-                        if (do_kl) kl_acc += (double)kl_term(mu, sigma, p.prior_mu, p.prior_sigma, p.kl_convention);
-                    }
-                    w[e] = wv; s2[e] = sv;
-                }
-                const uint4 o = make_uint4(pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]), pack_bf16(w[4], w[5]), pack_bf16(w[6], w[7]));
-                *reinterpret_cast<uint4*>(dst + chunk * (p.ng * 8) + row * 8) = o;
-                if (p.planes == 2) {
-                    const uint4 o2 = make_uint4(pack_bf16(s2[0], s2[1]), pack_bf16(s2[2], s2[3]), pack_bf16(s2[4], s2[5]), pack_bf16(s2[6], s2[7]));
-                    *reinterpret_cast<uint4*>(dst + p.ng * 64 + chunk * (p.ng * 8) + row * 8) = o2;
-                }
+        for (int e = 0; e < 8; ++e) {
+            const int kq = kb * 64 + chunk * 8 + e;                // packed input-channel index
+            float wv = 0.0f, sv = 0.0f;
+            if (n < g.N && kq < g.Cin) {
+                const int cin = (p.prev_hw > 1) ? ((kq % cprev) * p.prev_hw + kq / cprev) : kq;
+                const size_t wi = (size_t)n * g.K + (size_t)cin * g.KHW + tap;
+                const float mu = __ldg(p.w_mu + wi);
+                float sigma = 0.0f;
+                if (stoch || do_kl) sigma = softplus_sigma(__ldg(p.w_rho + wi));
+                if (LRT) { wv = mu; sv = sigma * sigma; }
+                else if (stoch) {
+                    const float e_ = p.eps_a ? __ldg(p.eps_a + wi) : normal1(wi, nkey);
+                    wv = mu + e_ * sigma;
+                } else wv = mu;
+                if (do_kl) kl_acc += (double)kl_term(mu, sigma, p.prior_mu, p.prior_sigma, p.kl_convention);
             }
+            w[e] = wv; s2[e] = sv;
         }
-        if (kb == 0 && threadIdx.x < p.ng) {
-            const int n = cb * p.ng + threadIdx.x;
-            const int npad = p.n_cblk * p.ng;
+        const uint4 o = make_uint4(pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]), pack_bf16(w[4], w[5]), pack_bf16(w[6], w[7]));
+        *reinterpret_cast<uint4*>(dst + chunk * (p.ng * 8) + row * 8) = o;
+        if (p.planes == 2) {
+            const uint4 o2 = make_uint4(pack_bf16(s2[0], s2[1]), pack_bf16(s2[2], s2[3]), pack_bf16(s2[4], s2[5]), pack_bf16(s2[6], s2[7]));
+            *reinterpret_cast<uint4*>(dst + p.ng * 64 + chunk * (p.ng * 8) + row * 8) = o2;
+        }
+    }
+    {   // bias: prepared (and its KL counted) by the first CTAs, one thread per channel
+        const int npad = p.n_cblk * p.ng;
+        for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < npad; n += gridDim.x * blockDim.x) {
             float bm = 0.0f, bv = 0.0f;
             if (p.has_bias && n < g.N) {
                 const float mu = __ldg(p.b_mu + n);
@@ -179,6 +178,8 @@ tap_gemm_kernel(const FusedArgs p, const __grid_constant__ CUtensorMap tm_a, con
         for (int q = 1; q < 4; ++q) { goh[q] = goh[0]; gow[q] = gow[0]; }
     }
 
+    long long* tr = p.trace ? p.trace + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+    if (tr && threadIdx.x == 0) tr[0] = clock64();
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
             mbar_init(smem_u32(&ctl->full[s]), 1);
@@ -193,6 +194,7 @@ tap_gemm_kernel(const FusedArgs p, const __grid_constant__ CUtensorMap tm_a, con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = ctl->tmem_base;
+    if (tr && threadIdx.x == 0) tr[1] = clock64();
 
     if (warp == 5) {
         // ======================= TMA producer ===================================
@@ -213,6 +215,7 @@ tap_gemm_kernel(const FusedArgs p, const __grid_constant__ CUtensorMap tm_a, con
 #pragma unroll
                     for (int q = 0; q < 4; ++q) if (tap[q] >= 0) bytes += sub_bytes;
                     mbar_arrive_expect_tx(bar, bytes);
+                    if (tr && it == 0) tr[2] = clock64();
                     const uint32_t st = base + tiles_off + (uint32_t)s * stage_bytes;
                     const int col = ipix * g.Cin + kb * 64;
                     tma_load_2d(st + a_off, &tm_a, col, m0, bar);
@@ -242,13 +245,14 @@ tap_gemm_kernel(const FusedArgs p, const __grid_constant__ CUtensorMap tm_a, con
                 const uint32_t ph = (uint32_t)(it / stages) & 1u;
                 mbar_wait(smem_u32(&ctl->full[s]), ph);
                 tc_fence_after();
+                if (tr && it == 0 && lane == 0) tr[3] = clock64();
                 if (lane == 0) {
                     const uint32_t st = base + tiles_off + (uint32_t)s * stage_bytes;
-#pragma unroll
+#pragma unroll 1
                     for (int q = 0; q < 4; ++q) {
                         if (tap[q] < 0) continue;
                         const uint32_t acc0 = (started >> q) & 1u;
-#pragma unroll
+#pragma unroll 1
                         for (int j = 0; j < 4; ++j) {
                             const uint64_t da = make_smem_desc_sw128(st + a_off + j * 32);
                             const uint64_t db = make_smem_desc(st + b_off + q * sub_bytes + j * 2 * (ng * 16), ng * 16, 128);
@@ -266,7 +270,7 @@ tap_gemm_kernel(const FusedArgs p, const __grid_constant__ CUtensorMap tm_a, con
                 __syncwarp();
             }
         }
-        if (lane == 0) umma_commit(smem_u32(&ctl->accum));
+        if (lane == 0) { umma_commit(smem_u32(&ctl->accum)); if (tr) tr[4] = clock64(); }
         __syncwarp();
         tc_fence_before();
     } else {
@@ -275,6 +279,7 @@ tap_gemm_kernel(const FusedArgs p, const __grid_constant__ CUtensorMap tm_a, con
         const bool bvalid = b < g.B;
         mbar_wait(smem_u32(&ctl->accum), 0u);
         tc_fence_after();
+        if (tr && threadIdx.x == 0) tr[5] = clock64();
         uint32_t started = 0;          // which column groups received at least one MMA (same schedule as warp 4)
         for (int ipix = 0; ipix < g.HW; ++ipix) {
             const int ih = ipix / g.W, iw = ipix - ih * g.W;
@@ -285,13 +290,14 @@ tap_gemm_kernel(const FusedArgs p, const __grid_constant__ CUtensorMap tm_a, con
         const NoiseKey nkey = effective_key(p.key, p.stream_base);
         const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
         const int npad = p.n_cblk * ng;
-        const bool stoch_lrt = two;
+        const int ohw_out = p.pool ? (g.OHW >> 2) : g.OHW;
+        const StoreCfg sc{p.y, p.y_sq, p.out_mode, p.out_pitch, g.N, p.act};
         if (p.pool) {
             // four column groups = the four pixels of one 2x2 window, 16 couts each
             float best[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) best[j] = -INFINITY;
-#pragma unroll
+#pragma unroll 1
             for (int q = 0; q < 4; ++q) {
                 float am[16], av[16];
                 tmem_ld16(lane_base + (uint32_t)(q * 16), am);
@@ -302,7 +308,7 @@ tap_gemm_kernel(const FusedArgs p, const __grid_constant__ CUtensorMap tm_a, con
                 for (int j = 0; j < 16; ++j) {
                     const int n = cb * 16 + j;
                     float val = (live ? am[j] : 0.0f) + p.bias_ws[n];
-                    if (stoch_lrt && bvalid && n < g.N) {
+                    if (two && bvalid && n < g.N) {
                         const size_t o = ((size_t)b * g.N + n) * g.OHW + pix;
                         const float var = 1e-16f + ((live ? av[j] : 0.0f) + p.bias_ws[npad + n]);
                         const float e_ = p.eps_a ? __ldg(p.eps_a + o) : normal1(o, nkey);
@@ -311,96 +317,38 @@ tap_gemm_kernel(const FusedArgs p, const __grid_constant__ CUtensorMap tm_a, con
                     best[j] = fmaxf(best[j], val);
                 }
             }
-            if (bvalid) {
-                float r[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) r[j] = apply_act(best[j], p.act);      // act is monotone: act(max) == max(act)
-                const int n0 = cb * 16;
-                if (p.out_mode == OUT_PACKED_BF16 && n0 + 16 <= g.N) {
-                    __nv_bfloat16* yo = reinterpret_cast<__nv_bfloat16*>(p.y) + (size_t)b * p.out_pitch + (size_t)pset * g.N + n0;
-                    uint4 v0 = make_uint4(pack_bf16(r[0], r[1]), pack_bf16(r[2], r[3]), pack_bf16(r[4], r[5]), pack_bf16(r[6], r[7]));
-                    uint4 v1 = make_uint4(pack_bf16(r[8], r[9]), pack_bf16(r[10], r[11]), pack_bf16(r[12], r[13]), pack_bf16(r[14], r[15]));
-                    reinterpret_cast<uint4*>(yo)[0] = v0; reinterpret_cast<uint4*>(yo)[1] = v1;
-                    if (p.y_sq) {
-                        __nv_bfloat16* ys = reinterpret_cast<__nv_bfloat16*>(p.y_sq) + (size_t)b * p.out_pitch + (size_t)pset * g.N + n0;
-                        uint4 s0 = make_uint4(pack_bf16(r[0] * r[0], r[1] * r[1]), pack_bf16(r[2] * r[2], r[3] * r[3]), pack_bf16(r[4] * r[4], r[5] * r[5]), pack_bf16(r[6] * r[6], r[7] * r[7]));
-                        uint4 s1 = make_uint4(pack_bf16(r[8] * r[8], r[9] * r[9]), pack_bf16(r[10] * r[10], r[11] * r[11]), pack_bf16(r[12] * r[12], r[13] * r[13]), pack_bf16(r[14] * r[14], r[15] * r[15]));
-                        reinterpret_cast<uint4*>(ys)[0] = s0; reinterpret_cast<uint4*>(ys)[1] = s1;
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int n = n0 + j;
-                        if (n >= g.N) continue;
-                        if (p.out_mode == OUT_PACKED_BF16) {
-                            const size_t o = (size_t)b * p.out_pitch + (size_t)pset * g.N + n;
-                            reinterpret_cast<__nv_bfloat16*>(p.y)[o] = __float2bfloat16_rn(r[j]);
-                            if (p.y_sq) reinterpret_cast<__nv_bfloat16*>(p.y_sq)[o] = __float2bfloat16_rn(r[j] * r[j]);
-                        } else if (p.out_mode == OUT_ROWMAJOR_F32) {
-                            reinterpret_cast<float*>(p.y)[((size_t)b * (g.OHW >> 2) + pset) * g.N + n] = r[j];
-                        } else {   // NCHW fp32, pooled map
-                            reinterpret_cast<float*>(p.y)[((size_t)b * g.N + n) * (g.OHW >> 2) + pset] = r[j];
-                        }
-                    }
-                }
-            }
+            if (bvalid) store_row16(sc, b, pset, cb * 16, best, ohw_out);      // act is monotone: act(max) == max(act)
         } else {
             const bool live = started & 1u;
-            const int pix = pset;
 #pragma unroll 1
             for (int c0 = 0; c0 < 64; c0 += 16) {
                 float am[16], av[16];
                 tmem_ld16(lane_base + (uint32_t)c0, am);
                 if (two) tmem_ld16(lane_base + 64u + (uint32_t)c0, av);
                 if (!bvalid) continue;
-                float r[16];
                 const int n0 = cb * 64 + c0;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const int n = n0 + j;
                     float val = (live ? am[j] : 0.0f) + p.bias_ws[n];
-                    if (stoch_lrt && n < g.N) {
-                        const size_t o = ((size_t)b * g.N + n) * g.OHW + pix;
+                    if (two && n < g.N) {
+                        const size_t o = ((size_t)b * g.N + n) * g.OHW + pset;
                         const float var = 1e-16f + ((live ? av[j] : 0.0f) + p.bias_ws[npad + n]);
                         const float e_ = p.eps_a ? __ldg(p.eps_a + o) : normal1(o, nkey);
                         val = val + sqrtf(var) * e_;
                     }
-                    r[j] = apply_act(val, p.act);
+                    am[j] = val;
                 }
-                if (p.out_mode == OUT_PACKED_BF16 && n0 + 16 <= g.N) {
-                    __nv_bfloat16* yo = reinterpret_cast<__nv_bfloat16*>(p.y) + (size_t)b * p.out_pitch + (size_t)pix * g.N + n0;
-                    uint4 v0 = make_uint4(pack_bf16(r[0], r[1]), pack_bf16(r[2], r[3]), pack_bf16(r[4], r[5]), pack_bf16(r[6], r[7]));
-                    uint4 v1 = make_uint4(pack_bf16(r[8], r[9]), pack_bf16(r[10], r[11]), pack_bf16(r[12], r[13]), pack_bf16(r[14], r[15]));
-                    reinterpret_cast<uint4*>(yo)[0] = v0; reinterpret_cast<uint4*>(yo)[1] = v1;
-                    if (p.y_sq) {
-                        __nv_bfloat16* ys = reinterpret_cast<__nv_bfloat16*>(p.y_sq) + (size_t)b * p.out_pitch + (size_t)pix * g.N + n0;
-                        uint4 s0 = make_uint4(pack_bf16(r[0] * r[0], r[1] * r[1]), pack_bf16(r[2] * r[2], r[3] * r[3]), pack_bf16(r[4] * r[4], r[5] * r[5]), pack_bf16(r[6] * r[6], r[7] * r[7]));
-                        uint4 s1 = make_uint4(pack_bf16(r[8] * r[8], r[9] * r[9]), pack_bf16(r[10] * r[10], r[11] * r[11]), pack_bf16(r[12] * r[12], r[13] * r[13]), pack_bf16(r[14] * r[14], r[15] * r[15]));
-                        reinterpret_cast<uint4*>(ys)[0] = s0; reinterpret_cast<uint4*>(ys)[1] = s1;
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int n = n0 + j;
-                        if (n >= g.N) continue;
-                        if (p.out_mode == OUT_PACKED_BF16) {
-                            const size_t o = (size_t)b * p.out_pitch + (size_t)pix * g.N + n;
-                            reinterpret_cast<__nv_bfloat16*>(p.y)[o] = __float2bfloat16_rn(r[j]);
-                            if (p.y_sq) reinterpret_cast<__nv_bfloat16*>(p.y_sq)[o] = __float2bfloat16_rn(r[j] * r[j]);
-                        } else if (p.out_mode == OUT_ROWMAJOR_F32) {
-                            reinterpret_cast<float*>(p.y)[((size_t)b * g.OHW + pix) * g.N + n] = r[j];
-                        } else {
-                            reinterpret_cast<float*>(p.y)[((size_t)b * g.N + n) * g.OHW + pix] = r[j];
-                        }
-                    }
-                }
+                store_row16(sc, b, pset, n0, am, ohw_out);
             }
         }
+        if (tr && threadIdx.x == 0) tr[6] = clock64();
         tc_fence_before();
     }
     __syncthreads();
     tc_fence_after();
     if (warp == 4) tmem_dealloc(tmem, tmem_cols);
+    if (tr && threadIdx.x == 128) tr[7] = clock64();
 }
 
 // ------------------------------------------------------------- host side
@@ -455,8 +403,10 @@ inline cudaError_t launch_fused(FusedArgs a, const void* x, const void* x_sq, cu
         if (!make_act_tmap(&tma2, x_sq, g.B, g.HW * g.Cin, a.in_pitch)) { *why = "cuTensorMapEncodeTiled failed (A^2)"; return cudaErrorInvalidValue; }
     } else tma2 = tma;
     {
-        int grid = a.n_cblk * a.n_kblk;
+        const long items = (long)a.taps * a.n_cblk * a.n_kblk * a.ng * 8;
+        int grid = (int)((items + 255) / 256);
         if (grid > 2048) grid = 2048;
+        if (grid < 1) grid = 1;
         if (lrt) tap_prep_kernel<BBB_VARIANT_LRT><<<grid, 256, 0, st>>>(a);
         else     tap_prep_kernel<BBB_VARIANT_BBB><<<grid, 256, 0, st>>>(a);
         cudaError_t e = cudaGetLastError();

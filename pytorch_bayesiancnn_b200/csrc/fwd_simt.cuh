@@ -25,7 +25,7 @@ struct FwdArgs {
     int sample, kl_convention, has_bias, act;
 };
 
-__device__ __forceinline__ float apply_act(float v, int act) {
+__device__ __noinline__ float apply_act(float v, int act) {
     if (act == BBB_ACT_SOFTPLUS) return v > 20.0f ? v : log1pf(expf(v));   // nn.Softplus(beta=1, threshold=20)
     if (act == BBB_ACT_RELU) return fmaxf(v, 0.0f);
     return v;

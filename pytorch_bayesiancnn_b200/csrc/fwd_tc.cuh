@@ -161,6 +161,43 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     return *reinterpret_cast<const uint32_t*>(&h);
 }
 
+enum { OUT_PACKED_BF16 = 0, OUT_ROWMAJOR_F32 = 1, OUT_NCHW_F32 = 2 };
+
+// Apply the fused activation to 16 consecutive output channels [n0, n0+16) of image b at
+// output position `pos` (pixel, or pooled window) and store them in the requested layout.
+struct StoreCfg { void* y; void* y_sq; int out_mode, out_pitch, N, act; };
+__device__ __noinline__ void store_row16(const StoreCfg p, int b, int pos, int n0, float (&v)[16], int ohw_out) {
+    const int N = p.N;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.act);
+    if (p.out_mode == OUT_PACKED_BF16 && n0 + 16 <= N) {
+        const size_t off = (size_t)b * p.out_pitch + (size_t)pos * N + n0;
+        uint4* yo = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) + off);
+        yo[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        yo[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+        if (p.y_sq) {
+            uint4* ys = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y_sq) + off);
+            ys[0] = make_uint4(pack_bf16(v[0] * v[0], v[1] * v[1]), pack_bf16(v[2] * v[2], v[3] * v[3]), pack_bf16(v[4] * v[4], v[5] * v[5]), pack_bf16(v[6] * v[6], v[7] * v[7]));
+            ys[1] = make_uint4(pack_bf16(v[8] * v[8], v[9] * v[9]), pack_bf16(v[10] * v[10], v[11] * v[11]), pack_bf16(v[12] * v[12], v[13] * v[13]), pack_bf16(v[14] * v[14], v[15] * v[15]));
+        }
+        return;
+    }
+#pragma unroll 1
+    for (int j = 0; j < 16; ++j) {
+        const int n = n0 + j;
+        if (n >= N) break;
+        if (p.out_mode == OUT_PACKED_BF16) {
+            const size_t o = (size_t)b * p.out_pitch + (size_t)pos * N + n;
+            reinterpret_cast<__nv_bfloat16*>(p.y)[o] = __float2bfloat16_rn(v[j]);
+            if (p.y_sq) reinterpret_cast<__nv_bfloat16*>(p.y_sq)[o] = __float2bfloat16_rn(v[j] * v[j]);
+        } else if (p.out_mode == OUT_ROWMAJOR_F32) {
+            reinterpret_cast<float*>(p.y)[((size_t)b * ohw_out + pos) * N + n] = v[j];
+        } else {
+            reinterpret_cast<float*>(p.y)[((size_t)b * N + n) * ohw_out + pos] = v[j];
+        }
+    }
+}
+
 // ------------------------------------------------------------ (P) weight prep
 // One CTA per (n-tile, k-block) 64x64 tile (grid-stride).  256 threads: item = (row, 8-wide
 // K chunk); consecutive threads take consecutive rows so the 16-byte writes are contiguous.
@@ -173,59 +210,57 @@ weight_prep_kernel(const TcArgs p) {
     const NoiseKey nkey = effective_key(p.key, p.stream_base);
     const bool stoch = p.sample != 0;
     const bool do_kl = p.kl_out != nullptr;
-    const int n_items = p.n_tiles * p.k_blocks;
     const int npad = p.n_tiles * TC_BN;
+    constexpr int PER_TILE = TC_BN * (TC_BK / 8);                   // (row, 8-wide K chunk) items per tile
+    const long n_items = (long)p.n_tiles * p.k_blocks * PER_TILE;
     double kl_acc = 0.0;
-
-    for (int tile = blockIdx.x; tile < n_items; tile += gridDim.x) {
+    for (long gi = (long)blockIdx.x * blockDim.x + threadIdx.x; gi < n_items; gi += (long)gridDim.x * blockDim.x) {
+        const int tile = (int)(gi / PER_TILE), item = (int)(gi - (long)tile * PER_TILE);
         const int nt = tile / p.k_blocks, kb = tile - nt * p.k_blocks;
         __nv_bfloat16* dst = p.wtiles + (size_t)tile * p.planes * TC_TILE_ELEMS;
-        for (int item = threadIdx.x; item < TC_BN * (TC_BK / 8); item += blockDim.x) {
-            const int row = item & (TC_BN - 1), chunk = item >> 6;
-            const int n = nt * TC_BN + row, k0 = kb * TC_BK + chunk * 8;
-            float w[8], s2[8];
+        const int row = item & (TC_BN - 1), chunk = item >> 6;
+        const int n = nt * TC_BN + row, k0 = kb * TC_BK + chunk * 8;
+        float w[8], s2[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int k = k0 + e;
-                float wv = 0.0f, sv = 0.0f;
-                if (n < g.N && k < g.K) {
-                    const size_t wi = (size_t)n * g.K + k;
-                    const float mu = __ldg(p.w_mu + wi);
-                    float sigma = 0.0f;
-                    if (stoch || do_kl) sigma = softplus_sigma(__ldg(p.w_rho + wi));
-                    if (LRT) { wv = mu; sv = sigma * sigma; }
-                    else if (stoch) {
-                        const float e_ = p.eps_a ? __ldg(p.eps_a + wi) : normal1(wi, nkey);
-                        wv = mu + e_ * sigma;
-                    } else wv = mu;
-                    if (do_kl) kl_acc += (double)kl_term(mu, sigma, p.prior_mu, p.prior_sigma, p.kl_convention);
-                }
-                w[e] = wv; s2[e] = sv;
-            }
-            // canonical K-major core-matrix order inside the 8 KB tile: chunk*1024 + row*16 bytes
-            uint4 o = make_uint4(pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]), pack_bf16(w[4], w[5]), pack_bf16(w[6], w[7]));
-            *reinterpret_cast<uint4*>(dst + chunk * (TC_BN * 8) + row * 8) = o;
-            if (p.planes == 2) {
-                uint4 o2 = make_uint4(pack_bf16(s2[0], s2[1]), pack_bf16(s2[2], s2[3]), pack_bf16(s2[4], s2[5]), pack_bf16(s2[6], s2[7]));
-                *reinterpret_cast<uint4*>(dst + TC_TILE_ELEMS + chunk * (TC_BN * 8) + row * 8) = o2;
-            }
-        }
-        if (kb == 0 && threadIdx.x < TC_BN) {                     // bias slice of this n-tile
-            const int n = nt * TC_BN + threadIdx.x;
-            float bm = 0.0f, bv = 0.0f;
-            if (p.has_bias && n < g.N) {
-                const float mu = __ldg(p.b_mu + n);
-                const float sigma = (stoch || do_kl) ? softplus_sigma(__ldg(p.b_rho + n)) : 0.0f;
-                if (LRT) { bm = mu; bv = sigma * sigma; }
+        for (int e = 0; e < 8; ++e) {
+            const int k = k0 + e;
+            float wv = 0.0f, sv = 0.0f;
+            if (n < g.N && k < g.K) {
+                const size_t wi = (size_t)n * g.K + k;
+                const float mu = __ldg(p.w_mu + wi);
+                float sigma = 0.0f;
+                if (stoch || do_kl) sigma = softplus_sigma(__ldg(p.w_rho + wi));
+                if (LRT) { wv = mu; sv = sigma * sigma; }
                 else if (stoch) {
-                    const float e_ = p.eps_b ? __ldg(p.eps_b + n) : normal1((uint64_t)g.N * g.K + n, nkey);
-                    bm = mu + e_ * sigma;
-                } else bm = mu;
+                    const float e_ = p.eps_a ? __ldg(p.eps_a + wi) : normal1(wi, nkey);
+                    wv = mu + e_ * sigma;
+                } else wv = mu;
                 if (do_kl) kl_acc += (double)kl_term(mu, sigma, p.prior_mu, p.prior_sigma, p.kl_convention);
             }
-            p.bias_ws[n] = bm;
-            p.bias_ws[npad + n] = bv;
+            w[e] = wv; s2[e] = sv;
         }
+        // canonical K-major core-matrix order inside the 8 KB tile: chunk*1024 + row*16 bytes
+        uint4 o = make_uint4(pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]), pack_bf16(w[4], w[5]), pack_bf16(w[6], w[7]));
+        *reinterpret_cast<uint4*>(dst + chunk * (TC_BN * 8) + row * 8) = o;
+        if (p.planes == 2) {
+            uint4 o2 = make_uint4(pack_bf16(s2[0], s2[1]), pack_bf16(s2[2], s2[3]), pack_bf16(s2[4], s2[5]), pack_bf16(s2[6], s2[7]));
+            *reinterpret_cast<uint4*>(dst + TC_TILE_ELEMS + chunk * (TC_BN * 8) + row * 8) = o2;
+        }
+    }
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < npad; n += gridDim.x * blockDim.x) {   // bias
+        float bm = 0.0f, bv = 0.0f;
+        if (p.has_bias && n < g.N) {
+            const float mu = __ldg(p.b_mu + n);
+            const float sigma = (stoch || do_kl) ? softplus_sigma(__ldg(p.b_rho + n)) : 0.0f;
+            if (LRT) { bm = mu; bv = sigma * sigma; }
+            else if (stoch) {
+                const float e_ = p.eps_b ? __ldg(p.eps_b + n) : normal1((uint64_t)g.N * g.K + n, nkey);
+                bm = mu + e_ * sigma;
+            } else bm = mu;
+            if (do_kl) kl_acc += (double)kl_term(mu, sigma, p.prior_mu, p.prior_sigma, p.kl_convention);
+        }
+        p.bias_ws[n] = bm;
+        p.bias_ws[npad + n] = bv;
     }
     if (do_kl) {
         const double tot = block_sum(kl_acc, red);
@@ -345,12 +380,12 @@ gemm_tc_kernel(const TcArgs p, const int stages) {
         const NoiseKey nkey = effective_key(p.key, p.stream_base);
         const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
         const int npad = p.n_tiles * TC_BN;
-        float* __restrict__ y = reinterpret_cast<float*>(p.y);
         const int ohw_out = p.pool ? (g.OHW >> 2) : g.OHW;
         const int opix = p.pool ? pwin : pix;
+        const StoreCfg sc{p.y, p.y_sq, p.out_mode, p.out_pitch, g.N, p.act};
 #pragma unroll 1
         for (int c0 = 0; c0 < TC_BN; c0 += 16) {
-            float am[16], av[16], r[16];
+            float am[16], av[16];
             tmem_ld16(lane_base + (uint32_t)c0, am);
             if (two) tmem_ld16(lane_base + 64u + (uint32_t)c0, av);
 #pragma unroll
@@ -372,33 +407,10 @@ gemm_tc_kernel(const TcArgs p, const int stages) {
                     val = fmaxf(val, __shfl_xor_sync(0xffffffffu, val, 1));
                     val = fmaxf(val, __shfl_xor_sync(0xffffffffu, val, 2));
                 }
-                r[j] = apply_act(val, p.act);
+                am[j] = val;
             }
             if (!mvalid || (p.pool && (threadIdx.x & 3))) continue;
-            const int nb = n0 + c0;
-            if (p.out_mode == 0 && nb + 16 <= g.N) {
-                __nv_bfloat16* yo = reinterpret_cast<__nv_bfloat16*>(p.y) + (size_t)bimg * p.out_pitch + (size_t)opix * g.N + nb;
-                reinterpret_cast<uint4*>(yo)[0] = make_uint4(pack_bf16(r[0], r[1]), pack_bf16(r[2], r[3]), pack_bf16(r[4], r[5]), pack_bf16(r[6], r[7]));
-                reinterpret_cast<uint4*>(yo)[1] = make_uint4(pack_bf16(r[8], r[9]), pack_bf16(r[10], r[11]), pack_bf16(r[12], r[13]), pack_bf16(r[14], r[15]));
-                if (p.y_sq) {
-                    __nv_bfloat16* ys = reinterpret_cast<__nv_bfloat16*>(p.y_sq) + (size_t)bimg * p.out_pitch + (size_t)opix * g.N + nb;
-                    reinterpret_cast<uint4*>(ys)[0] = make_uint4(pack_bf16(r[0] * r[0], r[1] * r[1]), pack_bf16(r[2] * r[2], r[3] * r[3]), pack_bf16(r[4] * r[4], r[5] * r[5]), pack_bf16(r[6] * r[6], r[7] * r[7]));
-                    reinterpret_cast<uint4*>(ys)[1] = make_uint4(pack_bf16(r[8] * r[8], r[9] * r[9]), pack_bf16(r[10] * r[10], r[11] * r[11]), pack_bf16(r[12] * r[12], r[13] * r[13]), pack_bf16(r[14] * r[14], r[15] * r[15]));
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int n = nb + j;
-                    if (n >= g.N) continue;
-                    if (p.out_mode == 0) {
-                        const size_t o = (size_t)bimg * p.out_pitch + (size_t)opix * g.N + n;
-                        reinterpret_cast<__nv_bfloat16*>(p.y)[o] = __float2bfloat16_rn(r[j]);
-                        if (p.y_sq) reinterpret_cast<__nv_bfloat16*>(p.y_sq)[o] = __float2bfloat16_rn(r[j] * r[j]);
-                    } else {
-                        y[((size_t)bimg * g.N + n) * ohw_out + opix] = r[j];
-                    }
-                }
-            }
+            store_row16(sc, bimg, opix, n0 + c0, am, ohw_out);       // activation applied there (monotone: act(max) == max(act))
         }
         tc_fence_before();
     } else if (warp == 4) {
@@ -456,7 +468,8 @@ inline cudaError_t launch_fwd_tc(TcArgs a, cudaStream_t st, int n_sm, int* n_lau
     *n_launch = 0;
     const bool lrt = a.variant == BBB_VARIANT_LRT;
     if (!a.skip_prep) {
-        int grid = a.n_tiles * a.k_blocks;
+        const long items = (long)a.n_tiles * a.k_blocks * TC_BN * (TC_BK / 8);
+        int grid = (int)((items + 255) / 256);
         if (grid > 2048) grid = 2048;
         if (lrt) weight_prep_kernel<BBB_VARIANT_LRT><<<grid, 256, 0, st>>>(a);
         else     weight_prep_kernel<BBB_VARIANT_BBB><<<grid, 256, 0, st>>>(a);

@@ -127,7 +127,8 @@ def workspace(device, desc=None, owner=None) -> torch.Tensor:
     zeroed.  With `owner` (a layer): a private buffer sized by bbb_workspace_bytes(desc),
     which on the tcgen05 path also holds that layer's prepared bf16 operand tiles."""
     n = int(L.lib().bbb_workspace_bytes(C.byref(desc) if desc is not None else None))
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream, owner)
+    # a layer-private buffer is keyed by the layer only: zero-filled once, never re-created per stream/graph
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream if owner is None else None, owner)
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < n:
         ws = torch.zeros(n, dtype=torch.uint8, device=device)

@@ -113,11 +113,19 @@ def plan(children, x_shape):
 
 def run(steps, x: torch.Tensor):
     """Execute a planned chain.  Returns the network output (fp32)."""
-    lib = L.lib()
-    dev = x.device
-    B = x.shape[0]
     cur, cur_sq, cur_pitch = x.contiguous().float(), None, 0
-    for st in steps:
+    for i, st in enumerate(steps):
+        nxt = steps[i + 1].layer if i + 1 < len(steps) else None
+        cur, cur_sq, cur_pitch = run_step(st, nxt, cur, cur_sq, cur_pitch)
+    return cur
+
+
+def run_step(st, nxt, cur, cur_sq, cur_pitch):
+    """One fused layer call: (y, y_sq, pitch) = step(cur, cur_sq)."""
+    lib = L.lib()
+    dev = cur.device
+    B = cur.shape[0]
+    if True:
         m = st.layer
         lrt = m._variant == L.VARIANT_LRT
         stoch = True                                     # ModuleWrapper calls children with sample=True (SURVEY D6)
@@ -142,8 +150,7 @@ def run(steps, x: torch.Tensor):
         if st.out_layout == L.LAYOUT_PACKED_BF16:
             pitch = (cout * oh * ow + 7) // 8 * 8
             y = torch.empty(B, pitch, dtype=torch.bfloat16, device=dev)
-            nxt = steps[steps.index(st) + 1].layer
-            y_sq = torch.empty_like(y) if nxt._variant == L.VARIANT_LRT else None
+            y_sq = torch.empty_like(y) if (nxt is not None and nxt._variant == L.VARIANT_LRT) else None
         elif st.out_layout == L.LAYOUT_ROWMAJOR_F32:
             pitch, y, y_sq = 0, torch.empty(B, cout, dtype=torch.float32, device=dev), None
         else:
@@ -172,5 +179,4 @@ def run(steps, x: torch.Tensor):
             Fn._stream(dev))
         L.check(rc, "bbb_layer_forward_fused")
         m._kl_cache = (kl, m._versions(), torch.is_grad_enabled())
-        cur, cur_sq, cur_pitch = y, y_sq, pitch
-    return cur
+        return y, y_sq, pitch
