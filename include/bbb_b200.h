@@ -85,7 +85,9 @@ size_t bbb_workspace_bytes(const bbb_layer_desc* desc);
  * eps_a  : BBB: W_eps [Cout,Cin,kh,kw]; LRT: activation eps, shape of y.  NULL => Philox.
  * eps_b  : BBB: bias_eps [Cout]; LRT: unused.                             NULL => Philox.
  * Philox element index: BBB: flat OIHW index for W, |W| + c for bias;
- *                       LRT: flat NCHW index of y.
+ *                       LRT: NHWC-flat index of y, ((b*OH*OW + pixel)*Cout + c), i.e. the
+ *                       eps tensor is fill(numel).view(B,OH,OW,C).permute(0,3,1,2) -- four
+ *                       consecutive channels share one Philox call in every kernel.
  * stream_base: nullable DEVICE pointer; when set the effective Philox stream is
  *          stream_id + *stream_base, read by the kernel at run time -- this is how a
  *          captured CUDA graph draws fresh noise on every replay (bbb_noise_advance). */

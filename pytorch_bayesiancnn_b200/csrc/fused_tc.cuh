@@ -46,7 +46,7 @@ __host__ __device__ inline size_t fused_wtile_elems(const FusedArgs& a) { return
 inline size_t fused_workspace_bytes(const Geom& g) {
     // worst case NG=16 padding of Cout, 2 planes
     const size_t cpad = (size_t)(g.N + 63) / 64 * 64, kpad = (size_t)(g.Cin + 63) / 64 * 64;
-    return cpad * kpad * g.KHW * 2 * 2 + 2 * cpad * 4;
+    return cpad * kpad * g.KHW * 2 * 2 + 16384 /* zero sub-tile */ + 2 * cpad * 4;
 }
 
 // ------------------------------------------------------------- (P) tap prep
@@ -89,13 +89,18 @@ tap_prep_kernel(const FusedArgs p) {
             }
             w[e] = wv; s2[e] = sv;
         }
+        // K-major SWIZZLE_128B image: row r = 128 contiguous bytes, its 16-byte chunk c stored at chunk (c ^ (r & 7))
+        const int sw = row * 64 + ((chunk ^ (row & 7)) << 3);
         const uint4 o = make_uint4(pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]), pack_bf16(w[4], w[5]), pack_bf16(w[6], w[7]));
-        *reinterpret_cast<uint4*>(dst + chunk * (p.ng * 8) + row * 8) = o;
+        *reinterpret_cast<uint4*>(dst + sw) = o;
         if (p.planes == 2) {
             const uint4 o2 = make_uint4(pack_bf16(s2[0], s2[1]), pack_bf16(s2[2], s2[3]), pack_bf16(s2[4], s2[5]), pack_bf16(s2[6], s2[7]));
-            *reinterpret_cast<uint4*>(dst + p.ng * 64 + chunk * (p.ng * 8) + row * 8) = o2;
+            *reinterpret_cast<uint4*>(dst + p.ng * 64 + sw) = o2;
         }
     }
+    // one all-zero sub-tile behind the real ones: staged for pool-window pixels whose tap is outside the kernel
+    for (long gi = (long)blockIdx.x * blockDim.x + threadIdx.x; gi < (long)(sub / 8); gi += (long)gridDim.x * blockDim.x)
+        reinterpret_cast<uint4*>(p.wtiles + (size_t)p.taps * p.n_cblk * p.n_kblk * sub)[gi] = make_uint4(0u, 0u, 0u, 0u);
     {   // bias: prepared (and its KL counted) by the first CTAs, one thread per channel
         const int npad = p.n_cblk * p.ng;
         for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < npad; n += gridDim.x * blockDim.x) {
@@ -135,6 +140,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
 struct FusedSmem {
     unsigned long long full[4], empty[4], accum;
     uint32_t tmem_base, pad;
+    float bias[64], bvar[64];       // this tile's 64 output columns
 };
 
 // tap linking output pixel (oh,ow) with input pixel (ih,iw); -1 if outside the kernel window
@@ -142,6 +148,24 @@ __device__ __forceinline__ int tap_of(const Geom& g, int oh, int ow, int ih, int
     const int r = ih - oh * g.SH + g.PH, s = iw - ow * g.SW + g.PW;
     if ((unsigned)r < (unsigned)g.KH && (unsigned)s < (unsigned)g.KW) return r * g.KW + s;
     return -1;
+}
+
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
+    uint32_t r0, r1, r2, r3;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
+}
+
+// LRT activation noise of image b, output pixel pix, channels [n, n+4): Philox element index is
+// the NHWC-flat index ((b*OHW + pix)*N + n), so four consecutive channels share one Philox call.
+__device__ __forceinline__ float4 act_noise4(const NoiseKey& k, int b, int pix, int n, int OHW, int N) {
+    const uint64_t o = ((uint64_t)b * OHW + pix) * N + n;
+    if ((N & 3) == 0) return normal4(o >> 2, k);
+    float4 z;
+    z.x = normal1(o, k); z.y = normal1(o + 1, k); z.z = normal1(o + 2, k); z.w = normal1(o + 3, k);
+    return z;
 }
 
 template <int VARIANT>
@@ -161,8 +185,9 @@ tap_gemm_kernel(const FusedArgs p, const __grid_constant__ CUtensorMap tm_a, con
     FusedSmem* ctl = reinterpret_cast<FusedSmem*>(sm);
     const uint32_t tiles_off = 1024u;
     const uint32_t stage_bytes = (uint32_t)planes * (TC_A_BYTES + TC_B_BYTES);
-    const uint32_t a_off = 0, a2_off = TC_A_BYTES, b_off = (uint32_t)planes * TC_A_BYTES;
+    const uint32_t a2_off = TC_A_BYTES, b_off = (uint32_t)planes * TC_A_BYTES;
     const uint32_t sub_bytes = (uint32_t)planes * ng * 128;          // one weight sub-tile (all planes)
+    float* ez = reinterpret_cast<float*>(sm + tiles_off + (size_t)stages * stage_bytes);   // [64][128] LRT noise
 
     // output tile -> (pixel set, cout block)
     const int n_tile = blockIdx.x, m0 = blockIdx.y * TC_BM;
@@ -188,6 +213,12 @@ tap_gemm_kernel(const FusedArgs p, const __grid_constant__ CUtensorMap tm_a, con
         mbar_init(smem_u32(&ctl->accum), 1);
         fence_barrier_init();
     }
+    if (threadIdx.x < 64) {                              // bias / bias variance of this tile's columns
+        const int c = threadIdx.x;
+        const int n = p.pool ? (cb * 16 + (c & 15)) : (cb * 64 + c);
+        ctl->bias[c] = p.bias_ws[n];
+        ctl->bvar[c] = p.bias_ws[p.n_cblk * ng + n];
+    }
     const uint32_t tmem_cols = two ? 128u : 64u;
     if (warp == 4) tmem_alloc(smem_u32(&ctl->tmem_base), tmem_cols);
     tc_fence_before();
@@ -200,70 +231,71 @@ tap_gemm_kernel(const FusedArgs p, const __grid_constant__ CUtensorMap tm_a, con
         // ======================= TMA producer ===================================
         if (lane == 0) {
             int it = 0;
+            const size_t sub_elems = (size_t)planes * ng * 64;
+            const uint32_t a_bytes = (uint32_t)planes * TC_A_BYTES;
+#pragma unroll 1
             for (int ipix = 0; ipix < g.HW; ++ipix) {
                 const int ih = ipix / g.W, iw = ipix - ih * g.W;
-                int tap[4], any = 0;
+                const __nv_bfloat16* src[4];
+                const __nv_bfloat16* zero_tile = p.wtiles + (size_t)p.taps * p.n_cblk * p.n_kblk * sub_elems;
+                bool any = false;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) { tap[q] = (q < groups) ? tap_of(g, goh[q], gow[q], ih, iw) : -1; any |= (tap[q] >= 0); }
+                for (int q = 0; q < 4; ++q) {
+                    const int tp = (q < groups) ? tap_of(g, goh[q], gow[q], ih, iw) : -1;
+                    src[q] = tp >= 0 ? p.wtiles + (size_t)(tp * p.n_cblk + cb) * p.n_kblk * sub_elems : nullptr;
+                    any |= tp >= 0;
+                }
                 if (!any) continue;
+                const uint32_t bytes = a_bytes + (uint32_t)groups * sub_bytes;
+                const int col0 = ipix * g.Cin;
+#pragma unroll 1
                 for (int kb = 0; kb < p.n_kblk; ++kb, ++it) {
                     const int s = it % stages;
-                    const uint32_t ph = (uint32_t)(it / stages) & 1u;
-                    mbar_wait(smem_u32(&ctl->empty[s]), ph ^ 1u);
+                    mbar_wait(smem_u32(&ctl->empty[s]), ((uint32_t)(it / stages) & 1u) ^ 1u);
                     const uint32_t bar = smem_u32(&ctl->full[s]);
-                    uint32_t bytes = (uint32_t)planes * TC_A_BYTES;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) if (tap[q] >= 0) bytes += sub_bytes;
                     mbar_arrive_expect_tx(bar, bytes);
                     if (tr && it == 0) tr[2] = clock64();
                     const uint32_t st = base + tiles_off + (uint32_t)s * stage_bytes;
-                    const int col = ipix * g.Cin + kb * 64;
-                    tma_load_2d(st + a_off, &tm_a, col, m0, bar);
-                    if (two) tma_load_2d(st + a2_off, &tm_a2, col, m0, bar);
+                    tma_load_2d(st, &tm_a, col0 + kb * 64, m0, bar);
+                    if (two) tma_load_2d(st + a2_off, &tm_a2, col0 + kb * 64, m0, bar);
+                    // weight planes: [plane][group][ng rows x 128 B]  -> every plane is one 64-row SW128 tile
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        if (tap[q] < 0) continue;
-                        const __nv_bfloat16* src = p.wtiles + ((size_t)(tap[q] * p.n_cblk + cb) * p.n_kblk + kb) * ((size_t)planes * ng * 64);
-                        bulk_g2s(st + b_off + q * sub_bytes, src, sub_bytes, bar);
+                        if (q >= groups) break;
+                        const __nv_bfloat16* sp = src[q] ? src[q] + (size_t)kb * sub_elems : zero_tile;
+                        bulk_g2s(st + b_off + q * (ng * 128), sp, ng * 128, bar);
+                        if (two) bulk_g2s(st + b_off + TC_B_BYTES + q * (ng * 128), sp + ng * 64, ng * 128, bar);
                     }
                 }
             }
         }
     } else if (warp == 4) {
         // ======================= MMA issuer =====================================
-        const uint32_t idesc = make_idesc_bf16(TC_BM, ng);
-        uint32_t started = 0;
+        const uint32_t idesc = make_idesc_bf16(TC_BM, 64);
+        // descriptors are linear in the (address >> 4) field: build them once, add offsets per MMA
+        const uint64_t dA0 = make_smem_desc_sw128(base + tiles_off);
+        const uint64_t dB0 = make_smem_desc_sw128(base + tiles_off + b_off);
         int it = 0;
+#pragma unroll 1
         for (int ipix = 0; ipix < g.HW; ++ipix) {
             const int ih = ipix / g.W, iw = ipix - ih * g.W;
-            int tap[4], any = 0;
+            bool live = false;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { tap[q] = (q < groups) ? tap_of(g, goh[q], gow[q], ih, iw) : -1; any |= (tap[q] >= 0); }
-            if (!any) continue;
+            for (int q = 0; q < 4; ++q) if (q < groups && tap_of(g, goh[q], gow[q], ih, iw) >= 0) live = true;
+            if (!live) continue;
+#pragma unroll 1
             for (int kb = 0; kb < p.n_kblk; ++kb, ++it) {
                 const int s = it % stages;
-                const uint32_t ph = (uint32_t)(it / stages) & 1u;
-                mbar_wait(smem_u32(&ctl->full[s]), ph);
+                mbar_wait(smem_u32(&ctl->full[s]), (uint32_t)(it / stages) & 1u);
                 tc_fence_after();
                 if (tr && it == 0 && lane == 0) tr[3] = clock64();
                 if (lane == 0) {
-                    const uint32_t st = base + tiles_off + (uint32_t)s * stage_bytes;
-#pragma unroll 1
-                    for (int q = 0; q < 4; ++q) {
-                        if (tap[q] < 0) continue;
-                        const uint32_t acc0 = (started >> q) & 1u;
-#pragma unroll 1
-                        for (int j = 0; j < 4; ++j) {
-                            const uint64_t da = make_smem_desc_sw128(st + a_off + j * 32);
-                            const uint64_t db = make_smem_desc(st + b_off + q * sub_bytes + j * 2 * (ng * 16), ng * 16, 128);
-                            umma_bf16(tmem + q * ng, da, db, idesc, (acc0 | j) ? 1u : 0u);
-                            if (two) {
-                                const uint64_t da2 = make_smem_desc_sw128(st + a2_off + j * 32);
-                                const uint64_t db2 = make_smem_desc(st + b_off + q * sub_bytes + ng * 128 + j * 2 * (ng * 16), ng * 16, 128);
-                                umma_bf16(tmem + 64u + q * ng, da2, db2, idesc, (acc0 | j) ? 1u : 0u);
-                            }
-                        }
-                        started |= 1u << q;
+                    const uint32_t so = ((uint32_t)s * stage_bytes) >> 4;
+                    const uint64_t da = dA0 + so, db = dB0 + so;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        umma_bf16(tmem, da + 2 * j, db + 2 * j, idesc, (it | j) ? 1u : 0u);
+                        if (two) umma_bf16(tmem + 64u, da + (a2_off >> 4) + 2 * j, db + (TC_B_BYTES >> 4) + 2 * j, idesc, (it | j) ? 1u : 0u);
                     }
                     umma_commit(smem_u32(&ctl->empty[s]));
                 }
@@ -277,69 +309,109 @@ tap_gemm_kernel(const FusedArgs p, const __grid_constant__ CUtensorMap tm_a, con
         // ======================= epilogue =======================================
         const int t = threadIdx.x, b = m0 + t;
         const bool bvalid = b < g.B;
-        mbar_wait(smem_u32(&ctl->accum), 0u);
-        tc_fence_after();
-        if (tr && threadIdx.x == 0) tr[5] = clock64();
-        uint32_t started = 0;          // which column groups received at least one MMA (same schedule as warp 4)
-        for (int ipix = 0; ipix < g.HW; ++ipix) {
+        const bool philox = two && !p.eps_a;
+        // (1) while the main loop runs: draw this row's LRT noise into smem (column-major, conflict free)
+        if (philox && bvalid) {
+            const NoiseKey nkey = effective_key(p.key, p.stream_base);
+#pragma unroll 1
+            for (int c4 = 0; c4 < 16; ++c4) {
+                const int c = c4 * 4;
+                const int q = p.pool ? (c >> 4) : 0;
+                const int n = p.pool ? (cb * 16 + (c & 15)) : (cb * 64 + c);
+                float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (n < g.N) z = act_noise4(nkey, b, goh[q] * g.OW + gow[q], n, g.OHW, g.N);
+                ez[(c + 0) * 128 + t] = z.x; ez[(c + 1) * 128 + t] = z.y;
+                ez[(c + 2) * 128 + t] = z.z; ez[(c + 3) * 128 + t] = z.w;
+            }
+        }
+        bool any_mma = false;          // did the schedule of warp 4 contain at least one step?
+#pragma unroll 1
+        for (int ipix = 0; ipix < g.HW && !any_mma; ++ipix) {
             const int ih = ipix / g.W, iw = ipix - ih * g.W;
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-                if (q < groups && tap_of(g, goh[q], gow[q], ih, iw) >= 0) started |= 1u << q;
+                if (q < groups && tap_of(g, goh[q], gow[q], ih, iw) >= 0) any_mma = true;
         }
-        const NoiseKey nkey = effective_key(p.key, p.stream_base);
+        // (2) accumulator ready
+        mbar_wait(smem_u32(&ctl->accum), 0u);
+        tc_fence_after();
+        if (tr && threadIdx.x == 0) tr[5] = clock64();
         const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
-        const int npad = p.n_cblk * ng;
         const int ohw_out = p.pool ? (g.OHW >> 2) : g.OHW;
-        const StoreCfg sc{p.y, p.y_sq, p.out_mode, p.out_pitch, g.N, p.act};
-        if (p.pool) {
-            // four column groups = the four pixels of one 2x2 window, 16 couts each
-            float best[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) best[j] = -INFINITY;
+        const int n_base = p.pool ? cb * 16 : cb * 64;
+        const int n_iter = p.pool ? 4 : 16;                // groups of 4 output channels
 #pragma unroll 1
-            for (int q = 0; q < 4; ++q) {
-                float am[16], av[16];
-                tmem_ld16(lane_base + (uint32_t)(q * 16), am);
-                if (two) tmem_ld16(lane_base + 64u + (uint32_t)(q * 16), av);
-                const bool live = (started >> q) & 1u;
-                const int pix = goh[q] * g.OW + gow[q];
+        for (int i4 = 0; i4 < n_iter; ++i4) {
+            float r[4];
+            if (p.pool) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int n = cb * 16 + j;
-                    float val = (live ? am[j] : 0.0f) + p.bias_ws[n];
-                    if (two && bvalid && n < g.N) {
-                        const size_t o = ((size_t)b * g.N + n) * g.OHW + pix;
-                        const float var = 1e-16f + ((live ? av[j] : 0.0f) + p.bias_ws[npad + n]);
-                        const float e_ = p.eps_a ? __ldg(p.eps_a + o) : normal1(o, nkey);
+                for (int u = 0; u < 4; ++u) r[u] = -INFINITY;
+#pragma unroll 1
+                for (int q = 0; q < 4; ++q) {
+                    const int c = q * 16 + i4 * 4;
+                    float am[4], av[4];
+                    tmem_ld4(lane_base + (uint32_t)c, am);
+                    if (two) tmem_ld4(lane_base + 64u + (uint32_t)c, av);
+                    const bool live = any_mma;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        float val = (live ? am[u] : 0.0f) + ctl->bias[c + u];
+                        if (two) {
+                            const float var = 1e-16f + ((live ? av[u] : 0.0f) + ctl->bvar[c + u]);
+                            float e_ = 0.0f;
+                            if (philox) e_ = ez[(c + u) * 128 + t];
+                            else if (bvalid && n_base + i4 * 4 + u < g.N)
+                                e_ = __ldg(p.eps_a + ((size_t)b * g.N + n_base + i4 * 4 + u) * g.OHW + goh[q] * g.OW + gow[q]);
+                            val = val + sqrtf(var) * e_;
+                        }
+                        r[u] = fmaxf(r[u], val);
+                    }
+                }
+            } else {
+                const int c = i4 * 4;
+                float am[4], av[4];
+                tmem_ld4(lane_base + (uint32_t)c, am);
+                if (two) tmem_ld4(lane_base + 64u + (uint32_t)c, av);
+                const bool live = any_mma;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float val = (live ? am[u] : 0.0f) + ctl->bias[c + u];
+                    if (two) {
+                        const float var = 1e-16f + ((live ? av[u] : 0.0f) + ctl->bvar[c + u]);
+                        float e_ = 0.0f;
+                        if (philox) e_ = ez[(c + u) * 128 + t];
+                        else if (bvalid && n_base + c + u < g.N)
+                            e_ = __ldg(p.eps_a + ((size_t)b * g.N + n_base + c + u) * g.OHW + pset);
                         val = val + sqrtf(var) * e_;
                     }
-                    best[j] = fmaxf(best[j], val);
+                    r[u] = val;
                 }
             }
-            if (bvalid) store_row16(sc, b, pset, cb * 16, best, ohw_out);      // act is monotone: act(max) == max(act)
-        } else {
-            const bool live = started & 1u;
-#pragma unroll 1
-            for (int c0 = 0; c0 < 64; c0 += 16) {
-                float am[16], av[16];
-                tmem_ld16(lane_base + (uint32_t)c0, am);
-                if (two) tmem_ld16(lane_base + 64u + (uint32_t)c0, av);
-                if (!bvalid) continue;
-                const int n0 = cb * 64 + c0;
+            if (!bvalid) continue;
+            const int n0 = n_base + i4 * 4;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int n = n0 + j;
-                    float val = (live ? am[j] : 0.0f) + p.bias_ws[n];
-                    if (two && n < g.N) {
-                        const size_t o = ((size_t)b * g.N + n) * g.OHW + pset;
-                        const float var = 1e-16f + ((live ? av[j] : 0.0f) + p.bias_ws[npad + n]);
-                        const float e_ = p.eps_a ? __ldg(p.eps_a + o) : normal1(o, nkey);
-                        val = val + sqrtf(var) * e_;
+            for (int u = 0; u < 4; ++u) r[u] = apply_act(r[u], p.act);      // act is monotone: act(max) == max(act)
+            if (p.out_mode == OUT_PACKED_BF16 && n0 + 4 <= g.N) {
+                const size_t off = (size_t)b * p.out_pitch + (size_t)pset * g.N + n0;
+                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.y) + off) = make_uint2(pack_bf16(r[0], r[1]), pack_bf16(r[2], r[3]));
+                if (p.y_sq)
+                    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.y_sq) + off) =
+                        make_uint2(pack_bf16(r[0] * r[0], r[1] * r[1]), pack_bf16(r[2] * r[2], r[3] * r[3]));
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int n = n0 + u;
+                    if (n >= g.N) continue;
+                    if (p.out_mode == OUT_PACKED_BF16) {
+                        const size_t o = (size_t)b * p.out_pitch + (size_t)pset * g.N + n;
+                        reinterpret_cast<__nv_bfloat16*>(p.y)[o] = __float2bfloat16_rn(r[u]);
+                        if (p.y_sq) reinterpret_cast<__nv_bfloat16*>(p.y_sq)[o] = __float2bfloat16_rn(r[u] * r[u]);
+                    } else if (p.out_mode == OUT_ROWMAJOR_F32) {
+                        reinterpret_cast<float*>(p.y)[((size_t)b * ohw_out + pset) * g.N + n] = r[u];
+                    } else {
+                        reinterpret_cast<float*>(p.y)[((size_t)b * g.N + n) * ohw_out + pset] = r[u];
                     }
-                    am[j] = val;
                 }
-                store_row16(sc, b, pset, n0, am, ohw_out);
             }
         }
         if (tr && threadIdx.x == 0) tr[6] = clock64();
@@ -414,7 +486,7 @@ inline cudaError_t launch_fused(FusedArgs a, const void* x, const void* x_sq, cu
         *n_launch += 1;
     }
     const int stages = 4;                                            // 96 KB (1 plane) / 192 KB (2 planes)
-    const size_t smem = 2048 + (size_t)stages * tc_stage_bytes(a.planes);
+    const size_t smem = 2048 + (size_t)stages * tc_stage_bytes(a.planes) + (a.planes == 2 ? 64 * 128 * 4 : 0);   // + LRT noise tile
     const int psets = a.pool ? (g.OH / 2) * (g.OW / 2) : g.OHW;
     dim3 grid(psets * a.n_cblk, (g.B + TC_BM - 1) / TC_BM);
     cudaError_t e;

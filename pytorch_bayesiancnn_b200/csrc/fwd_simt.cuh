@@ -214,7 +214,8 @@ fwd_simt_kernel(const FwdArgs p) {
             if (need_var) {
                 const float var = 1e-16f + (accv[i][j] + bias_v[j]);   // BBB_LRT/BBBConv.py:73-74
                 const float sd = sqrtf(var);
-                const float e = p.eps_a ? __ldg(p.eps_a + o) : normal1(o, nkey);
+                // Philox element index of the activation noise: NHWC-flat ((b*OHW + pix)*N + n)
+                const float e = p.eps_a ? __ldg(p.eps_a + o) : normal1(((uint64_t)b * g.OHW + pix) * g.N + n, nkey);
                 v = v + sd * e;                                       // BBB_LRT/BBBConv.py:79
                 if (p.act_std) p.act_std[o] = sd;
             }

@@ -398,7 +398,7 @@ gemm_tc_kernel(const TcArgs p, const int stages) {
                     if (two) {
                         const float var = 1e-16f + (av[j] + p.bias_ws[npad + n]);
                         const float sd = sqrtf(var);
-                        const float e_ = p.eps_a ? __ldg(p.eps_a + o) : normal1(o, nkey);
+                        const float e_ = p.eps_a ? __ldg(p.eps_a + o) : normal1(((uint64_t)bimg * g.OHW + pix) * g.N + n, nkey);
                         val = val + sd * e_;
                         if (p.act_std) p.act_std[o] = sd;
                     }

@@ -71,6 +71,16 @@ def test_philox_stream_matches_host_restatement(dev):
     assert abs(float(z.mean())) < 5e-3 and abs(float(z.std()) - 1) < 5e-3
 
 
+def _lrt_eps_like(bbb, y, seed, stream, dev):
+    """The activation noise an LRT kernel draws for output y: Philox element index is the
+    NHWC-flat index of y (include/bbb_b200.h), so fill(numel).view(B,OH,OW,C).permute(0,3,1,2)."""
+    z = bbb.philox_normal(y.numel(), seed, stream, 0, device=dev)
+    if y.dim() == 4:
+        B, C, H, W = y.shape
+        return z.view(B, H, W, C).permute(0, 3, 1, 2).contiguous()
+    return z.view_as(y)
+
+
 def test_in_kernel_philox_equals_external_draw(golden_layers, dev):
     """The eps a kernel draws itself == bbb_philox_normal_fill of the same (seed, stream):
     run once with in-kernel Philox, once feeding that stream as external eps."""
@@ -89,7 +99,7 @@ def test_in_kernel_philox_equals_external_draw(golden_layers, dev):
             if layer.use_bias:
                 eps.append(bbb.philox_normal(layer.bias_mu.numel(), seed, ctr, nw, device=dev))
         else:
-            eps = [bbb.philox_normal(y1.numel(), seed, ctr, 0, device=dev).view_as(y1)]
+            eps = [_lrt_eps_like(bbb, y1, seed, ctr, dev)]
         with torch.no_grad(), bbb.external_eps(eps):
             y2 = layer(x)
         assert scale_err(y1, y2) < 1e-6, name
@@ -315,7 +325,7 @@ def test_tc_philox_equals_external_draw(dev):
             eps = [bbb.philox_normal(nw, 77, 5, 0, device=dev).view_as(layer.W_mu),
                    bbb.philox_normal(96, 77, 5, nw, device=dev)]
         else:
-            eps = [bbb.philox_normal(y1.numel(), 77, 5, 0, device=dev).view_as(y1)]
+            eps = [_lrt_eps_like(bbb, y1, 77, 5, dev)]
         with torch.no_grad(), bbb.external_eps(eps):
             y2 = layer(x)
         assert scale_err(y1, y2) < 1e-6
