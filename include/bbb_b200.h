@@ -125,7 +125,12 @@ enum { BBB_LAYOUT_NCHW_F32 = 0,      /* reference layout: [B, C, H, W] fp32     
  *   in_pitch : elements per row of a packed input;  prev_hw: for a linear layer fed by a
  *              flattened HxW map, H*W of that map (reference feature order is c*HW + pix)
  *   y, y_sq  : output and (packed output, nullable) its square for a following LRT layer
- * Forward only (math = BBB_MATH_BF16_TC); eps / Philox / KL semantics as the unfused calls. */
+ * Forward only (math = BBB_MATH_BF16_TC); eps / Philox / KL semantics as the unfused calls.
+ * desc->reserved[0] splits the call so the parameter-only half can run on a side stream, off
+ * the activation critical path: BBB_FUSED_PREP_ONLY launches just the weight-prep kernel
+ * (sigma, eps, bf16 operand tiles, KL -> kl_out; x/y unused), BBB_FUSED_SKIP_PREP just the GEMM
+ * kernel (the caller orders it after the prep, e.g. with an event).  0 = both, in order. */
+enum { BBB_FUSED_PREP_ONLY = 1, BBB_FUSED_SKIP_PREP = 2 };
 int bbb_layer_forward_fused(const bbb_layer_desc* desc,
                             const void* x, const void* x_sq, int32_t in_layout, int32_t in_pitch, int32_t prev_hw,
                             const float* W_mu, const float* W_rho,

@@ -19,6 +19,7 @@ MATH_FP32, MATH_BF16_TC, MATH_AUTO = 0, 1, 2
 KL_REFERENCE, KL_TEXTBOOK = 0, 1
 ACT_NONE, ACT_SOFTPLUS, ACT_RELU = 0, 1, 2
 LAYOUT_NCHW_F32, LAYOUT_PACKED_BF16, LAYOUT_ROWMAJOR_F32 = 0, 1, 2
+FUSED_PREP_ONLY, FUSED_SKIP_PREP = 1, 2
 
 MATH_BY_NAME = {"fp32": MATH_FP32, "bf16": MATH_BF16_TC, "auto": MATH_AUTO}
 KL_BY_NAME = {"reference": KL_REFERENCE, "textbook": KL_TEXTBOOK}

@@ -72,7 +72,7 @@ int forward_impl(const bbb_layer_desc* d, bool linear, const void* x, const floa
         bbb::TcArgs a;
         a.wtiles = (__nv_bfloat16*)((char*)ws + kTcOffset);
         a.bias_ws = (float*)((char*)ws + kTcOffset + (size_t)bbb::tc_npad(g) * bbb::tc_kpad(g) * 4);
-        a.skip_prep = 0; a.y_sq = nullptr; a.out_mode = 2; a.out_pitch = 0; a.pool = 0;
+        a.skip_prep = 0; a.prep_only = 0; a.y_sq = nullptr; a.out_mode = 2; a.out_pitch = 0; a.pool = 0; a.trace = g_trace;
         a.g = g; a.x = x; a.w_mu = W_mu; a.w_rho = W_rho; a.b_mu = bias_mu; a.b_rho = bias_rho;
         a.y = y; a.kl_out = kl_out; a.act_std = act_std; a.eps_a = eps_a; a.eps_b = eps_b;
         a.key = bbb::make_key(seed, stream_id); a.stream_base = (const unsigned long long*)stream_base;
@@ -185,7 +185,9 @@ int bbb_layer_forward_fused(const bbb_layer_desc* d, const void* x, const void* 
                             uint64_t stream_id, const uint64_t* stream_base, void* ws, size_t ws_bytes, void* stream) {
     bbb::Geom g;
     if (int rc = check_desc(d, g, false)) return rc;
-    if (!x || !W_mu || !W_rho || !y) return fail(BBB_E_INVALID, "NULL tensor pointer");
+    const bool prep_only = (d->reserved[0] & BBB_FUSED_PREP_ONLY) != 0, skip_prep = (d->reserved[0] & BBB_FUSED_SKIP_PREP) != 0;
+    if (prep_only && skip_prep) return fail(BBB_E_INVALID, "PREP_ONLY and SKIP_PREP are exclusive");
+    if (!W_mu || !W_rho || (!prep_only && (!x || !y))) return fail(BBB_E_INVALID, "NULL tensor pointer");
     if (d->has_bias && (!bias_mu || !bias_rho)) return fail(BBB_E_INVALID, "has_bias set but bias pointers NULL");
     if (d->math == BBB_MATH_FP32) return fail(BBB_E_UNSUPPORTED, "the fused chain exists on the tcgen05 (bf16) path only");
     const int pool = d->pool_k != 0;
@@ -211,7 +213,7 @@ int bbb_layer_forward_fused(const bbb_layer_desc* d, const void* x, const void* 
         a.act_dtype = d->act_dtype; a.variant = d->variant;
         a.wtiles = (__nv_bfloat16*)((char*)ws + kTcOffset);
         a.bias_ws = (float*)((char*)ws + kTcOffset + (size_t)bbb::tc_npad(g) * bbb::tc_kpad(g) * 4);
-        a.skip_prep = 0; a.y_sq = y_sq; a.out_mode = out_mode == 1 ? 2 : out_mode; a.out_pitch = out_pitch; a.pool = pool;
+        a.trace = g_trace; a.skip_prep = skip_prep; a.prep_only = prep_only; a.y_sq = y_sq; a.out_mode = out_mode == 1 ? 2 : out_mode; a.out_pitch = out_pitch; a.pool = pool;
         cudaError_t e = bbb::launch_fwd_tc(a, st, sm_count(), &nl);
         if (e != cudaSuccess) return cuda_fail(e, "fused gather launch");
     } else if (in_layout == BBB_LAYOUT_PACKED_BF16) {
@@ -230,7 +232,7 @@ int bbb_layer_forward_fused(const bbb_layer_desc* d, const void* x, const void* 
         a.prev_hw = prev_hw; a.y = y; a.y_sq = y_sq; a.out_mode = out_mode; a.out_pitch = out_pitch; a.pool = pool;
         a.in_pitch = in_pitch; a.trace = g_trace;
         const char* why = "";
-        cudaError_t e = bbb::launch_fused(a, x, x_sq, st, &nl, &why);
+        cudaError_t e = bbb::launch_fused(a, x, x_sq, st, &nl, &why, !skip_prep, !prep_only);
         if (e != cudaSuccess) return fail(BBB_E_CUDA, "fused tap-GEMM launch: %s %s", cudaGetErrorString(e), why);
     } else {
         return fail(BBB_E_INVALID, "bad in_layout %d", in_layout);

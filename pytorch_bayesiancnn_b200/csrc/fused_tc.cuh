@@ -339,69 +339,69 @@ tap_gemm_kernel(const FusedArgs p, const __grid_constant__ CUtensorMap tm_a, con
         const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
         const int ohw_out = p.pool ? (g.OHW >> 2) : g.OHW;
         const int n_base = p.pool ? cb * 16 : cb * 64;
-        const int n_iter = p.pool ? 4 : 16;                // groups of 4 output channels
+        const int n_iter = p.pool ? 2 : 8;                 // groups of 8 output channels
 #pragma unroll 1
-        for (int i4 = 0; i4 < n_iter; ++i4) {
-            float r[4];
+        for (int i8 = 0; i8 < n_iter; ++i8) {
+            float r[8];
             if (p.pool) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) r[u] = -INFINITY;
+                for (int u = 0; u < 8; ++u) r[u] = -INFINITY;
 #pragma unroll 1
                 for (int q = 0; q < 4; ++q) {
-                    const int c = q * 16 + i4 * 4;
-                    float am[4], av[4];
-                    tmem_ld4(lane_base + (uint32_t)c, am);
-                    if (two) tmem_ld4(lane_base + 64u + (uint32_t)c, av);
-                    const bool live = any_mma;
+                    const int c = q * 16 + i8 * 8;
+                    float am[8], av[8];
+                    tmem_ld8(lane_base + (uint32_t)c, am);
+                    if (two) tmem_ld8(lane_base + 64u + (uint32_t)c, av);
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        float val = (live ? am[u] : 0.0f) + ctl->bias[c + u];
+                    for (int u = 0; u < 8; ++u) {
+                        float val = (any_mma ? am[u] : 0.0f) + ctl->bias[c + u];
                         if (two) {
-                            const float var = 1e-16f + ((live ? av[u] : 0.0f) + ctl->bvar[c + u]);
+                            const float var = 1e-16f + ((any_mma ? av[u] : 0.0f) + ctl->bvar[c + u]);
                             float e_ = 0.0f;
                             if (philox) e_ = ez[(c + u) * 128 + t];
-                            else if (bvalid && n_base + i4 * 4 + u < g.N)
-                                e_ = __ldg(p.eps_a + ((size_t)b * g.N + n_base + i4 * 4 + u) * g.OHW + goh[q] * g.OW + gow[q]);
-                            val = val + sqrtf(var) * e_;
+                            else if (bvalid && n_base + i8 * 8 + u < g.N)
+                                e_ = __ldg(p.eps_a + ((size_t)b * g.N + n_base + i8 * 8 + u) * g.OHW + goh[q] * g.OW + gow[q]);
+                            val = val + fast_sqrt(var) * e_;
                         }
                         r[u] = fmaxf(r[u], val);
                     }
                 }
             } else {
-                const int c = i4 * 4;
-                float am[4], av[4];
-                tmem_ld4(lane_base + (uint32_t)c, am);
-                if (two) tmem_ld4(lane_base + 64u + (uint32_t)c, av);
-                const bool live = any_mma;
+                const int c = i8 * 8;
+                float am[8], av[8];
+                tmem_ld8(lane_base + (uint32_t)c, am);
+                if (two) tmem_ld8(lane_base + 64u + (uint32_t)c, av);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    float val = (live ? am[u] : 0.0f) + ctl->bias[c + u];
+                for (int u = 0; u < 8; ++u) {
+                    float val = (any_mma ? am[u] : 0.0f) + ctl->bias[c + u];
                     if (two) {
-                        const float var = 1e-16f + ((live ? av[u] : 0.0f) + ctl->bvar[c + u]);
+                        const float var = 1e-16f + ((any_mma ? av[u] : 0.0f) + ctl->bvar[c + u]);
                         float e_ = 0.0f;
                         if (philox) e_ = ez[(c + u) * 128 + t];
                         else if (bvalid && n_base + c + u < g.N)
                             e_ = __ldg(p.eps_a + ((size_t)b * g.N + n_base + c + u) * g.OHW + pset);
-                        val = val + sqrtf(var) * e_;
+                        val = val + fast_sqrt(var) * e_;
                     }
                     r[u] = val;
                 }
             }
             if (!bvalid) continue;
-            const int n0 = n_base + i4 * 4;
+            const int n0 = n_base + i8 * 8;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) r[u] = apply_act(r[u], p.act);      // act is monotone: act(max) == max(act)
-            if (p.out_mode == OUT_PACKED_BF16 && n0 + 4 <= g.N) {
+            for (int u = 0; u < 8; ++u) r[u] = fast_act(r[u], p.act);       // act is monotone: act(max) == max(act)
+            if (p.out_mode == OUT_PACKED_BF16 && n0 + 8 <= g.N) {
                 const size_t off = (size_t)b * p.out_pitch + (size_t)pset * g.N + n0;
-                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.y) + off) = make_uint2(pack_bf16(r[0], r[1]), pack_bf16(r[2], r[3]));
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) + off) =
+                    make_uint4(pack_bf16(r[0], r[1]), pack_bf16(r[2], r[3]), pack_bf16(r[4], r[5]), pack_bf16(r[6], r[7]));
                 if (p.y_sq)
-                    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.y_sq) + off) =
-                        make_uint2(pack_bf16(r[0] * r[0], r[1] * r[1]), pack_bf16(r[2] * r[2], r[3] * r[3]));
+                    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y_sq) + off) =
+                        make_uint4(pack_bf16(r[0] * r[0], r[1] * r[1]), pack_bf16(r[2] * r[2], r[3] * r[3]),
+                                   pack_bf16(r[4] * r[4], r[5] * r[5]), pack_bf16(r[6] * r[6], r[7] * r[7]));
             } else {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
+#pragma unroll 1
+                for (int u = 0; u < 8; ++u) {
                     const int n = n0 + u;
-                    if (n >= g.N) continue;
+                    if (n >= g.N) break;
                     if (p.out_mode == OUT_PACKED_BF16) {
                         const size_t o = (size_t)b * p.out_pitch + (size_t)pset * g.N + n;
                         reinterpret_cast<__nv_bfloat16*>(p.y)[o] = __float2bfloat16_rn(r[u]);
@@ -459,7 +459,8 @@ inline bool fused_supported(const Geom& g, int pool) {
     return true;
 }
 
-inline cudaError_t launch_fused(FusedArgs a, const void* x, const void* x_sq, cudaStream_t st, int* n_launch, const char** why) {
+inline cudaError_t launch_fused(FusedArgs a, const void* x, const void* x_sq, cudaStream_t st, int* n_launch, const char** why,
+                                bool do_prep = true, bool do_gemm = true) {
     const Geom& g = a.g;
     *n_launch = 0;
     a.planes = tc_planes(a.variant, a.sample);
@@ -469,12 +470,14 @@ inline cudaError_t launch_fused(FusedArgs a, const void* x, const void* x_sq, cu
     a.taps = g.KHW;
     const bool lrt = a.variant == BBB_VARIANT_LRT;
     CUtensorMap tma, tma2;
-    if (!make_act_tmap(&tma, x, g.B, g.HW * g.Cin, a.in_pitch)) { *why = "cuTensorMapEncodeTiled failed (A)"; return cudaErrorInvalidValue; }
-    if (a.planes == 2) {
+    if (!do_gemm) { memset(&tma, 0, sizeof(tma)); tma2 = tma; }
+    else if (!make_act_tmap(&tma, x, g.B, g.HW * g.Cin, a.in_pitch)) { *why = "cuTensorMapEncodeTiled failed (A)"; return cudaErrorInvalidValue; }
+    if (!do_gemm) {
+    } else if (a.planes == 2) {
         if (!x_sq) { *why = "LRT fused layer needs the squared activation"; return cudaErrorInvalidValue; }
         if (!make_act_tmap(&tma2, x_sq, g.B, g.HW * g.Cin, a.in_pitch)) { *why = "cuTensorMapEncodeTiled failed (A^2)"; return cudaErrorInvalidValue; }
     } else tma2 = tma;
-    {
+    if (do_prep) {
         const long items = (long)a.taps * a.n_cblk * a.n_kblk * a.ng * 8;
         int grid = (int)((items + 255) / 256);
         if (grid > 2048) grid = 2048;
@@ -485,6 +488,7 @@ inline cudaError_t launch_fused(FusedArgs a, const void* x, const void* x_sq, cu
         if (e != cudaSuccess) return e;
         *n_launch += 1;
     }
+    if (!do_gemm) return cudaSuccess;
     const int stages = 4;                                            // 96 KB (1 plane) / 192 KB (2 planes)
     const size_t smem = 2048 + (size_t)stages * tc_stage_bytes(a.planes) + (a.planes == 2 ? 64 * 128 * 4 : 0);   // + LRT noise tile
     const int psets = a.pool ? (g.OH / 2) * (g.OW / 2) : g.OHW;

@@ -46,9 +46,11 @@ struct TcArgs {
     __nv_bfloat16* wtiles;   // [n_tiles][k_blocks][planes][64*64]
     float* bias_ws;          // [2][Npad]: row 0 = bias (BBB: sampled; LRT: mu), row 1 = LRT sigma_b^2
     int n_tiles, k_blocks, planes;
-    int skip_prep;
+    int skip_prep, prep_only;
+    int stage_x;             // stage the tile's input images in shared memory (small per-tile footprint)
     // fused epilogue (first layer of a fused chain): 2x2 max-pool + packed bf16 output
     void* y_sq; int out_mode, out_pitch, pool;     // out_mode: 0 packed bf16 [B,(pix,c)], 2 NCHW fp32 (default)
+    long long* trace;                              // debug: per-CTA clock64 checkpoints (nullptr in production)
 };
 
 constexpr int TC_BM = 128, TC_BN = 64, TC_BK = 64;
@@ -61,7 +63,7 @@ inline int tc_planes(int variant, int sample) { return (variant == BBB_VARIANT_L
 inline size_t tc_stage_bytes(int planes) { return (size_t)planes * (TC_A_BYTES + TC_B_BYTES); }
 inline int tc_kpad(const Geom& g) { return (g.K + TC_BK - 1) / TC_BK * TC_BK; }
 inline int tc_npad(const Geom& g) { return (g.N + TC_BN - 1) / TC_BN * TC_BN; }
-inline size_t tc_fixed_smem(const Geom& g) { return 2048 /*two 1 KB alignment slacks*/ + 256 /*barriers*/ + (size_t)tc_kpad(g) * 8; }
+inline size_t tc_fixed_smem(const Geom& g) { return 2048 /*two 1 KB alignment slacks*/ + 1024 /*barriers + bias*/ + (size_t)tc_kpad(g) * 8; }
 inline int tc_stages(const Geom& g, int planes) {
     const long avail = (long)TC_SMEM_LIMIT - (long)tc_fixed_smem(g);
     long s = avail / (long)tc_stage_bytes(planes);
@@ -163,13 +165,35 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 
 enum { OUT_PACKED_BF16 = 0, OUT_ROWMAJOR_F32 = 1, OUT_NCHW_F32 = 2 };
 
+// Epilogue math of the bf16 path: MUFU-based, a handful of instructions (the exact versions in
+// fwd_simt.cuh cost ~100 instructions per value and the epilogue warps run at IPC ~0.25).
+// |error| <= ~1e-7 absolute: far inside the bf16 rounding of the values they feed.
+__device__ __forceinline__ float fast_act(float v, int act) {
+    if (act == BBB_ACT_SOFTPLUS) return fmaxf(v, 0.0f) + __logf(1.0f + __expf(-fabsf(v)));   // == nn.Softplus(1, 20)
+    if (act == BBB_ACT_RELU) return fmaxf(v, 0.0f);
+    return v;
+}
+__device__ __forceinline__ float fast_sqrt(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // Apply the fused activation to 16 consecutive output channels [n0, n0+16) of image b at
 // output position `pos` (pixel, or pooled window) and store them in the requested layout.
 struct StoreCfg { void* y; void* y_sq; int out_mode, out_pitch, N, act; };
 __device__ __noinline__ void store_row16(const StoreCfg p, int b, int pos, int n0, float (&v)[16], int ohw_out) {
     const int N = p.N;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.act);
+    for (int j = 0; j < 16; ++j) v[j] = fast_act(v[j], p.act);
     if (p.out_mode == OUT_PACKED_BF16 && n0 + 16 <= N) {
         const size_t off = (size_t)b * p.out_pitch + (size_t)pos * N + n0;
         uint4* yo = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) + off);
@@ -272,10 +296,17 @@ weight_prep_kernel(const TcArgs p) {
 struct TcSmem {      // barrier block at the start of dynamic smem (after 1024-alignment)
     unsigned long long full[4], empty[4], accum;
     uint32_t tmem_base, pad;
+    float bias[64], bvar[64];
 };
 
+// Largest number of images a 128-row tile can touch (rows ordered image-major).
+__host__ __device__ inline int tc_tile_images(int OHW) {
+    if (TC_BM % OHW == 0) return TC_BM / OHW;          // tiles start on image boundaries
+    return OHW >= TC_BM ? 2 : (TC_BM + OHW - 1) / OHW + 1;
+}
+
 template <int VARIANT>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 2)
 gemm_tc_kernel(const TcArgs p, const int stages) {
     constexpr bool LRT = VARIANT == BBB_VARIANT_LRT;
     extern __shared__ uint8_t smem_raw[];
@@ -288,16 +319,21 @@ gemm_tc_kernel(const TcArgs p, const int stages) {
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (base - raw);
     TcSmem* ctl = reinterpret_cast<TcSmem*>(sm);
-    int2* ktab = reinterpret_cast<int2*>(sm + 256);
+    int2* ktab = reinterpret_cast<int2*>(sm + 1024);
     const int kpad = p.k_blocks * TC_BK;
-    const uint32_t tiles_off = (256u + (uint32_t)kpad * 8u + 1023u) & ~1023u;
+    const uint32_t tiles_off = (1024u + (uint32_t)kpad * 8u + 1023u) & ~1023u;
     const uint32_t stage_bytes = (uint32_t)planes * (TC_A_BYTES + TC_B_BYTES);
     // stage layout: [A (16K)] [A^2 (16K, LRT)] [B planes (8K each)]
     const uint32_t a_off = 0, a2_off = TC_A_BYTES, b_off = (uint32_t)planes * TC_A_BYTES;
+    float* xs = reinterpret_cast<float*>(sm + tiles_off + (size_t)stages * stage_bytes);   // staged input images (stage_x)
 
     const int n_tile = blockIdx.x, m_tile = blockIdx.y;
     const int m0 = m_tile * TC_BM, n0 = n_tile * TC_BN;
+    const int chw = g.Cin * g.HW;
+    const int img0 = m0 / g.OHW;
 
+    long long* tr = p.trace ? p.trace + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+    if (tr && threadIdx.x == 0) tr[0] = clock64();
     // ---- one-time setup ------------------------------------------------------
     for (int k = threadIdx.x; k < kpad; k += blockDim.x) {
         int2 e;
@@ -309,24 +345,45 @@ gemm_tc_kernel(const TcArgs p, const int stages) {
         } else { e.x = 0; e.y = 0x7fff7fff; }
         ktab[k] = e;
     }
+    if (p.stage_x) {
+        // the tile's input images, loaded once and coalesced; the im2col gather then reads shared memory
+        // (LDS latency ~30 cycles) instead of issuing 64 dependent-latency global loads per thread and k-block
+        const int last = min(m0 + TC_BM - 1, g.M - 1) / g.OHW;
+        const int nflt = (last - img0 + 1) * chw;
+        const float* src = reinterpret_cast<const float*>(p.x) + (size_t)img0 * chw;
+        if (((reinterpret_cast<uintptr_t>(src) | (uintptr_t)(nflt * 4)) & 15u) == 0) {
+            for (int i = threadIdx.x; i < (nflt >> 2); i += blockDim.x)
+                reinterpret_cast<float4*>(xs)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+        } else {
+            for (int i = threadIdx.x; i < nflt; i += blockDim.x) xs[i] = __ldg(src + i);
+        }
+    }
+    if (threadIdx.x < 64) {
+        const int npad_ = p.n_tiles * TC_BN;
+        ctl->bias[threadIdx.x] = p.bias_ws[n0 + threadIdx.x];
+        ctl->bvar[threadIdx.x] = p.bias_ws[npad_ + n0 + threadIdx.x];
+    }
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
-            mbar_init(smem_u32(&ctl->full[s]), 128 + 1);      // 128 A-producer threads + the TMA thread
+            mbar_init(smem_u32(&ctl->full[s]), 256 + 1);      // 256 A-producer threads + the TMA thread
             mbar_init(smem_u32(&ctl->empty[s]), 1);           // one tcgen05.commit
         }
         mbar_init(smem_u32(&ctl->accum), 1);
         fence_barrier_init();
     }
     const uint32_t tmem_cols = two ? 128u : 64u;
-    if (warp == 4) tmem_alloc(smem_u32(&ctl->tmem_base), tmem_cols);
+    if (warp == 8) tmem_alloc(smem_u32(&ctl->tmem_base), tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = ctl->tmem_base;
+    if (tr && threadIdx.x == 0) tr[1] = clock64();
 
-    if (warp < 4) {
+    if (warp < 8) {
         // ================= A producers (then epilogue) =========================
-        const int t = threadIdx.x;                      // row of the tile == TMEM lane
+        // 8 warps: thread -> (row = t & 127, half = t >> 7); a half owns 4 of the 8 K-chunks of every k-block in the
+        // main loop and 32 of the 64 output columns in the epilogue (warps w and w+4 share TMEM lanes 32*(w&3)..)
+        const int t = threadIdx.x & 127, half = threadIdx.x >> 7;   // row of the tile == TMEM lane
         const int m = m0 + t;
         const bool mvalid = m < g.M;
         int ih0 = 0, iw0 = 0; long xb = 0;
@@ -342,16 +399,16 @@ gemm_tc_kernel(const TcArgs p, const int stages) {
                 pix = oh * g.OW + ow;
             } else { oh = pix / g.OW; ow = pix - oh * g.OW; }
             ih0 = oh * g.SH - g.PH; iw0 = ow * g.SW - g.PW;
-            xb = (long)bimg * g.Cin * g.HW + (long)ih0 * g.W + iw0;
+            xb = (long)(p.stage_x ? bimg - img0 : bimg) * chw + (long)ih0 * g.W + iw0;
         }
-        const float* __restrict__ xp = reinterpret_cast<const float*>(p.x);
+        const float* __restrict__ xp = p.stage_x ? xs : reinterpret_cast<const float*>(p.x);
         for (int kb = 0; kb < p.k_blocks; ++kb) {
             const int s = kb % stages;
             const uint32_t ph = (uint32_t)(kb / stages) & 1u;
             mbar_wait(smem_u32(&ctl->empty[s]), ph ^ 1u);
             uint8_t* st = sm + tiles_off + (size_t)s * stage_bytes;
 #pragma unroll 2
-            for (int c8 = 0; c8 < 8; ++c8) {
+            for (int c8 = half * 4; c8 < half * 4 + 4; ++c8) {
                 float v[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
@@ -359,7 +416,7 @@ gemm_tc_kernel(const TcArgs p, const int stages) {
                     const int ih = ih0 + (kt.y >> 16), iw = iw0 + (kt.y & 0xffff);
                     float val = 0.0f;
                     if (mvalid && (unsigned)ih < (unsigned)g.H && (unsigned)iw < (unsigned)g.W)
-                        val = __ldg(xp + xb + kt.x);
+                        val = xp[xb + kt.x];
                     v[e] = val;
                 }
                 const uint4 o = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
@@ -372,33 +429,50 @@ gemm_tc_kernel(const TcArgs p, const int stages) {
             }
             fence_proxy_async();                        // generic-proxy stores -> visible to the tensor core
             mbar_arrive(smem_u32(&ctl->full[s]));
+            if (tr && threadIdx.x == 0 && kb == 0) tr[2] = clock64();
         }
+        if (tr && threadIdx.x == 0) tr[3] = clock64();
 
         // ================= epilogue ============================================
+        // (1) LRT noise for this row, 8 columns at a time, drawn while the last MMAs drain
+        const bool philox = two && !p.eps_a;
+        const NoiseKey nkey = effective_key(p.key, p.stream_base);
         mbar_wait(smem_u32(&ctl->accum), 0u);
         tc_fence_after();
-        const NoiseKey nkey = effective_key(p.key, p.stream_base);
-        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
-        const int npad = p.n_tiles * TC_BN;
+        if (tr && threadIdx.x == 0) tr[5] = clock64();
+        const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         const int ohw_out = p.pool ? (g.OHW >> 2) : g.OHW;
         const int opix = p.pool ? pwin : pix;
-        const StoreCfg sc{p.y, p.y_sq, p.out_mode, p.out_pitch, g.N, p.act};
+        const bool writer = mvalid && !(p.pool && (threadIdx.x & 3));
 #pragma unroll 1
-        for (int c0 = 0; c0 < TC_BN; c0 += 16) {
-            float am[16], av[16];
-            tmem_ld16(lane_base + (uint32_t)c0, am);
-            if (two) tmem_ld16(lane_base + 64u + (uint32_t)c0, av);
+        for (int c0 = half * 32; c0 < half * 32 + 32; c0 += 8) {
+            float am[8], av[8], ez[8];
+            tmem_ld8(lane_base + (uint32_t)c0, am);
+            if (two) tmem_ld8(lane_base + 64u + (uint32_t)c0, av);
+            const int nb = n0 + c0;
+            if (philox) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int n = n0 + c0 + j;
+                for (int h = 0; h < 2; ++h) {
+                    float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (mvalid && nb + 4 * h < g.N) {
+                        const uint64_t o4 = ((uint64_t)bimg * g.OHW + pix) * g.N + nb + 4 * h;   // NHWC-flat element index
+                        if ((g.N & 3) == 0) z = normal4(o4 >> 2, nkey);
+                        else { z.x = normal1(o4, nkey); z.y = normal1(o4 + 1, nkey); z.z = normal1(o4 + 2, nkey); z.w = normal1(o4 + 3, nkey); }
+                    }
+                    ez[4 * h] = z.x; ez[4 * h + 1] = z.y; ez[4 * h + 2] = z.z; ez[4 * h + 3] = z.w;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int n = nb + j;
                 float val = -INFINITY;
                 if (mvalid && n < g.N) {
-                    const size_t o = ((size_t)bimg * g.N + n) * g.OHW + pix;
-                    val = am[j] + p.bias_ws[n];
+                    val = am[j] + ctl->bias[c0 + j];
                     if (two) {
-                        const float var = 1e-16f + (av[j] + p.bias_ws[npad + n]);
-                        const float sd = sqrtf(var);
-                        const float e_ = p.eps_a ? __ldg(p.eps_a + o) : normal1(((uint64_t)bimg * g.OHW + pix) * g.N + n, nkey);
+                        const size_t o = ((size_t)bimg * g.N + n) * g.OHW + pix;
+                        const float var = 1e-16f + (av[j] + ctl->bvar[c0 + j]);
+                        const float sd = p.act_std ? sqrtf(var) : fast_sqrt(var);
+                        const float e_ = philox ? ez[j] : __ldg(p.eps_a + o);
                         val = val + sd * e_;
                         if (p.act_std) p.act_std[o] = sd;
                     }
@@ -407,13 +481,35 @@ gemm_tc_kernel(const TcArgs p, const int stages) {
                     val = fmaxf(val, __shfl_xor_sync(0xffffffffu, val, 1));
                     val = fmaxf(val, __shfl_xor_sync(0xffffffffu, val, 2));
                 }
-                am[j] = val;
+                am[j] = fast_act(val, p.act);           // act is monotone: act(max) == max(act)
             }
-            if (!mvalid || (p.pool && (threadIdx.x & 3))) continue;
-            store_row16(sc, bimg, opix, n0 + c0, am, ohw_out);       // activation applied there (monotone: act(max) == max(act))
+            if (!writer) continue;
+            if (p.out_mode == OUT_PACKED_BF16 && nb + 8 <= g.N) {
+                const size_t off = (size_t)bimg * p.out_pitch + (size_t)opix * g.N + nb;
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) + off) =
+                    make_uint4(pack_bf16(am[0], am[1]), pack_bf16(am[2], am[3]), pack_bf16(am[4], am[5]), pack_bf16(am[6], am[7]));
+                if (p.y_sq)
+                    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y_sq) + off) =
+                        make_uint4(pack_bf16(am[0] * am[0], am[1] * am[1]), pack_bf16(am[2] * am[2], am[3] * am[3]),
+                                   pack_bf16(am[4] * am[4], am[5] * am[5]), pack_bf16(am[6] * am[6], am[7] * am[7]));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int n = nb + j;
+                    if (n >= g.N) continue;
+                    if (p.out_mode == OUT_PACKED_BF16) {
+                        const size_t o = (size_t)bimg * p.out_pitch + (size_t)opix * g.N + n;
+                        reinterpret_cast<__nv_bfloat16*>(p.y)[o] = __float2bfloat16_rn(am[j]);
+                        if (p.y_sq) reinterpret_cast<__nv_bfloat16*>(p.y_sq)[o] = __float2bfloat16_rn(am[j] * am[j]);
+                    } else {
+                        reinterpret_cast<float*>(p.y)[((size_t)bimg * g.N + n) * ohw_out + opix] = am[j];
+                    }
+                }
+            }
         }
+        if (tr && threadIdx.x == 0) tr[6] = clock64();
         tc_fence_before();
-    } else if (warp == 4) {
+    } else if (warp == 8) {
         // ================= MMA issuer ==========================================
         constexpr uint32_t idesc = make_idesc_bf16(TC_BM, TC_BN);
         for (int kb = 0; kb < p.k_blocks; ++kb) {
@@ -457,7 +553,8 @@ gemm_tc_kernel(const TcArgs p, const int stages) {
     }
     __syncthreads();
     tc_fence_after();
-    if (warp == 4) tmem_dealloc(tmem, tmem_cols);
+    if (warp == 8) tmem_dealloc(tmem, tmem_cols);
+    if (tr && threadIdx.x == 256) tr[7] = clock64();
 }
 
 inline cudaError_t launch_fwd_tc(TcArgs a, cudaStream_t st, int n_sm, int* n_launch) {
@@ -478,18 +575,25 @@ inline cudaError_t launch_fwd_tc(TcArgs a, cudaStream_t st, int n_sm, int* n_lau
         *n_launch += 1;
         a.kl_out = nullptr;
     }
-    const int stages = tc_stages(g, a.planes);
-    const size_t smem = tc_fixed_smem(g) + (size_t)stages * tc_stage_bytes(a.planes);
+    if (a.prep_only) return cudaSuccess;
+    int stages = tc_stages(g, a.planes);
+    // short K loops (AlexNet conv1: 6 k-blocks) gain nothing from a deep ring; two stages let two CTAs share an
+    // SM (2 x (2 x 48 KB) for LRT), which hides the gather latency of one CTA behind the other and halves the waves
+    if (a.k_blocks <= 8 && stages > 2) stages = 2;
+    size_t smem = tc_fixed_smem(g) + (size_t)stages * tc_stage_bytes(a.planes);
+    const size_t xs_bytes = (size_t)tc_tile_images(g.OHW) * g.Cin * g.HW * 4;
+    a.stage_x = (xs_bytes <= 32 * 1024 && smem + xs_bytes <= (size_t)TC_SMEM_LIMIT) ? 1 : 0;
+    if (a.stage_x) smem += xs_bytes;
     dim3 grid(a.n_tiles, (g.M + TC_BM - 1) / TC_BM);
     cudaError_t e;
     if (lrt) {
         e = cudaFuncSetAttribute(gemm_tc_kernel<BBB_VARIANT_LRT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        gemm_tc_kernel<BBB_VARIANT_LRT><<<grid, 192, smem, st>>>(a, stages);
+        gemm_tc_kernel<BBB_VARIANT_LRT><<<grid, 320, smem, st>>>(a, stages);
     } else {
         e = cudaFuncSetAttribute(gemm_tc_kernel<BBB_VARIANT_BBB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        gemm_tc_kernel<BBB_VARIANT_BBB><<<grid, 192, smem, st>>>(a, stages);
+        gemm_tc_kernel<BBB_VARIANT_BBB><<<grid, 320, smem, st>>>(a, stages);
     }
     (void)n_sm;
     e = cudaGetLastError();

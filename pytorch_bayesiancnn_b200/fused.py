@@ -24,7 +24,7 @@ from . import functional as Fn
 
 class _Step:
     __slots__ = ("layer", "act", "pool", "conv", "in_shape", "in_layout", "prev_hw", "out_layout", "out_chw",
-                 "eps_shape", "linear")
+                 "eps_shape", "linear", "batch")
 
 
 def _act_code(m):
@@ -47,7 +47,7 @@ def plan(children, x_shape):
     from .modules import _BayesLayer, FlattenLayer
     if len(x_shape) != 4:
         return None
-    _, c, h, w = x_shape
+    batch, c, h, w = x_shape
     state = ("nchw", c, h, w)
     steps = []
     i, n = 0, len(children)
@@ -57,6 +57,7 @@ def plan(children, x_shape):
             return None
         st = _Step()
         st.layer = m
+        st.batch = batch
         st.conv = m._conv_geometry()
         st.linear = st.conv is None
         lay, c, h, w = state
@@ -111,27 +112,82 @@ def plan(children, x_shape):
     return steps
 
 
-def run(steps, x: torch.Tensor):
-    """Execute a planned chain.  Returns the network output (fp32)."""
+_side_streams: dict = {}
+
+
+def _side_stream(dev):
+    st = _side_streams.get(dev.index)
+    if st is None:
+        st = _side_streams[dev.index] = torch.cuda.Stream(device=dev)
+    return st
+
+
+def run(steps, x: torch.Tensor, overlap_prep: bool = True):
+    """Execute a planned chain.  Returns (network output fp32, summed KL 0-dim tensor).
+
+    The parameter-only half of every layer (softplus / eps / bf16 operand tiles / KL) is
+    launched on a side stream up front and joined by events, so that -- eagerly or inside a
+    captured graph -- it runs beside the first layers instead of on the activation critical
+    path; the GEMM halves then run back to back on the calling stream."""
+    dev = x.device
+    kls = torch.empty(len(steps), dtype=torch.float32, device=dev)
+    noise = [_draw_noise(st, x.shape[0], dev) for st in steps]
+    if overlap_prep:
+        main, side = torch.cuda.current_stream(dev), _side_stream(dev)
+        side.wait_stream(main)
+        events = []
+        with torch.cuda.stream(side):
+            for i, st in enumerate(steps):
+                run_step(st, None, None, None, 0, kl=kls[i], noise=noise[i], phase=L.FUSED_PREP_ONLY)
+                ev = torch.cuda.Event()
+                ev.record(side)
+                events.append(ev)
     cur, cur_sq, cur_pitch = x.contiguous().float(), None, 0
     for i, st in enumerate(steps):
         nxt = steps[i + 1].layer if i + 1 < len(steps) else None
-        cur, cur_sq, cur_pitch = run_step(st, nxt, cur, cur_sq, cur_pitch)
-    return cur
+        if overlap_prep:
+            main.wait_event(events[i])
+            cur, cur_sq, cur_pitch = run_step(st, nxt, cur, cur_sq, cur_pitch, kl=kls[i], noise=noise[i],
+                                              phase=L.FUSED_SKIP_PREP)
+        else:
+            cur, cur_sq, cur_pitch = run_step(st, nxt, cur, cur_sq, cur_pitch, kl=kls[i], noise=noise[i])
+    return cur, kls.sum()
 
 
-def run_step(st, nxt, cur, cur_sq, cur_pitch):
-    """One fused layer call: (y, y_sq, pitch) = step(cur, cur_sq)."""
+def _draw_noise(st, B, dev):
+    """(eps_a, eps_b, seed, stream_id, base) for one layer call, consuming the external-eps
+    queue / the Philox stream counter exactly like the unfused layer would."""
+    m = st.layer
+    eps_a = eps_b = None
+    seed = stream_id = 0
+    base = None
+    if Fn.external_eps_active():
+        if m._variant == L.VARIANT_LRT:
+            eps_a = Fn._pop_eps((B,) + st.eps_shape if not st.linear else (B, st.eps_shape[0]), dev)
+        else:
+            eps_a = Fn._pop_eps(m.W_mu.shape, dev)
+            if m.use_bias:
+                eps_b = Fn._pop_eps(m.bias_mu.shape, dev)
+    else:
+        seed, stream_id = Fn.next_stream()
+        base = Fn._noise.base
+    return eps_a, eps_b, seed, stream_id, base
+
+
+def run_step(st, nxt, cur, cur_sq, cur_pitch, kl=None, noise=None, phase=0):
+    """One fused layer call: (y, y_sq, pitch) = step(cur, cur_sq).  phase: 0 = prep + GEMM,
+    FUSED_PREP_ONLY / FUSED_SKIP_PREP = one half (see include/bbb_b200.h)."""
     lib = L.lib()
-    dev = cur.device
-    B = cur.shape[0]
+    m = st.layer
+    dev = m.W_mu.device
+    B = st.batch if cur is None else cur.shape[0]
     if True:
-        m = st.layer
         lrt = m._variant == L.VARIANT_LRT
         stoch = True                                     # ModuleWrapper calls children with sample=True (SURVEY D6)
         cin, h, w = st.in_shape
         d = L.LayerDesc()
         d.batch, d.in_channels, d.in_h, d.in_w = B, cin, h, w
+        in_pitch = cur_pitch if st.in_layout == L.LAYOUT_NCHW_F32 else (cin * h * w + 7) // 8 * 8
         if st.linear:
             d.out_channels, d.kernel_h, d.kernel_w = m.out_features, 1, 1
             d.stride_h = d.stride_w = d.dil_h = d.dil_w = 1
@@ -145,9 +201,12 @@ def run_step(st, nxt, cur, cur_sq, cur_pitch):
         d.kl_convention = L.KL_BY_NAME[m.kl_convention]
         d.epilogue_act = st.act
         d.pool_k = d.pool_s = 2 if st.pool else 0
+        d.reserved[0] = phase
         d.prior_mu, d.prior_sigma = float(m.prior_mu), float(m.prior_sigma)
         cout, oh, ow = st.out_chw
-        if st.out_layout == L.LAYOUT_PACKED_BF16:
+        if phase == L.FUSED_PREP_ONLY:
+            pitch, y, y_sq = (cout * oh * ow + 7) // 8 * 8 if st.out_layout == L.LAYOUT_PACKED_BF16 else 0, None, None
+        elif st.out_layout == L.LAYOUT_PACKED_BF16:
             pitch = (cout * oh * ow + 7) // 8 * 8
             y = torch.empty(B, pitch, dtype=torch.bfloat16, device=dev)
             y_sq = torch.empty_like(y) if (nxt is not None and nxt._variant == L.VARIANT_LRT) else None
@@ -155,28 +214,19 @@ def run_step(st, nxt, cur, cur_sq, cur_pitch):
             pitch, y, y_sq = 0, torch.empty(B, cout, dtype=torch.float32, device=dev), None
         else:
             pitch, y, y_sq = 0, torch.empty(B, cout, oh, ow, dtype=torch.float32, device=dev), None
-        kl = torch.empty((), dtype=torch.float32, device=dev)
-        eps_a = eps_b = None
-        seed = stream_id = 0
-        base = None
-        if stoch:
-            if Fn.external_eps_active():
-                if lrt:
-                    eps_a = Fn._pop_eps((B,) + st.eps_shape if not st.linear else (B, st.eps_shape[0]), dev)
-                else:
-                    eps_a = Fn._pop_eps(m.W_mu.shape, dev)
-                    if m.use_bias:
-                        eps_b = Fn._pop_eps(m.bias_mu.shape, dev)
-            else:
-                seed, stream_id = Fn.next_stream()
-                base = Fn._noise.base
+        if kl is None:
+            kl = torch.empty((), dtype=torch.float32, device=dev)
+        if noise is None:
+            noise = _draw_noise(st, B, dev)
+        eps_a, eps_b, seed, stream_id, base = noise
         ws = Fn.workspace(dev, d, id(m))
         rc = lib.bbb_layer_forward_fused(
-            C.byref(d), Fn._ptr(cur), Fn._ptr(cur_sq), st.in_layout, cur_pitch, st.prev_hw,
+            C.byref(d), Fn._ptr(cur), Fn._ptr(cur_sq), st.in_layout, in_pitch, st.prev_hw,
             Fn._ptr(m.W_mu), Fn._ptr(m.W_rho), Fn._ptr(m.bias_mu), Fn._ptr(m.bias_rho),
             Fn._ptr(y), Fn._ptr(y_sq), st.out_layout, pitch, Fn._ptr(kl), Fn._ptr(eps_a), Fn._ptr(eps_b),
             C.c_uint64(seed), C.c_uint64(stream_id), Fn._ptr(base), Fn._ptr(ws), C.c_size_t(ws.numel()),
             Fn._stream(dev))
         L.check(rc, "bbb_layer_forward_fused")
-        m._kl_cache = (kl, m._versions(), torch.is_grad_enabled())
+        if phase != L.FUSED_SKIP_PREP:
+            m._kl_cache = (kl, m._versions(), torch.is_grad_enabled())
         return y, y_sq, pitch

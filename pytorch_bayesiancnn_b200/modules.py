@@ -67,7 +67,7 @@ class ModuleWrapper(nn.Module):
         if steps is None:
             return None
         try:
-            return fused.run(steps, x)
+            return fused.run(steps, x)          # (output, summed KL)
         except L.EngineError as e:
             if "code -2" not in str(e):                    # anything but BBB_E_UNSUPPORTED is a real error
                 raise
@@ -77,10 +77,11 @@ class ModuleWrapper(nn.Module):
     def forward(self, x):
         out = self._try_fused(x)
         if out is not None:
-            x = out
-        else:
-            for child in self.children():
-                x = child(x)
+            # the fused chain already reduced the per-layer KL scalars (each layer's kl_loss() still
+            # returns its own term); same value as the loop below, one launch instead of one per layer
+            return out
+        for child in self.children():
+            x = child(x)
         kl = 0.0
         for m in self.modules():
             if hasattr(m, "kl_loss"):

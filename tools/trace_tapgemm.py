@@ -20,18 +20,18 @@ lib._handle  # noqa
 fn = C.CDLL(L.LIB_PATH).bbb_debug_set_trace
 fn.argtypes = [C.c_void_p]
 trace = torch.zeros(4096 * 8, dtype=torch.int64, device=dev)
-names = ["entry", "setup", "tma0", "full0", "lastmma", "accum", "epi_end", "exit"]
+names = ["entry", "setup", "tma0|kb0", "full0|prod_end", "lastmma", "accum", "epi_end", "exit"]
 with torch.no_grad():
     for rep in range(3):
         cur, sq, pitch = x, None, 0
         for i, st in enumerate(steps):
             nxt = steps[i + 1].layer if i + 1 < len(steps) else None
             trace.zero_()
-            fn(C.c_void_p(trace.data_ptr()) if i > 0 else None)
+            fn(C.c_void_p(trace.data_ptr()))
             torch.cuda.synchronize()
             cur, sq, pitch = fused.run_step(st, nxt, cur, sq, pitch)
             torch.cuda.synchronize()
-            if i > 0 and rep == 2:
+            if rep == 2:
                 t = trace.view(-1, 8).cpu()
                 t = t[t[:, 0] != 0]
                 rel = (t - t[:, :1]).double()
