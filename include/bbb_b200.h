@@ -112,7 +112,10 @@ int bbb_linear_forward(const bbb_layer_desc* desc, const void* x,
 
 /* Activation layouts of the fused tcgen05 chain (bbb_layer_forward_fused). */
 enum { BBB_LAYOUT_NCHW_F32 = 0,      /* reference layout: [B, C, H, W] fp32                       */
-       BBB_LAYOUT_PACKED_BF16 = 1,   /* [B, pitch] bf16, column = (h*W + w)*C + c (NHWC flattened) */
+       BBB_LAYOUT_PACKED_BF16 = 1,   /* "tiled packed" bf16: the [B, F] matrix, F = H*W*C, column = (h*W + w)*C + c,
+                                        C % 64 == 0, stored as [ceil(B/128)][F/64][128 rows x 128 B] with every 16 KB
+                                        block in the K-major SWIZZLE_128B shared-memory image (chunk c of row r at
+                                        chunk c ^ (r & 7)); pitch arguments carry F */
        BBB_LAYOUT_ROWMAJOR_F32 = 2 };/* [B, OH*OW, Cout] fp32 (logits when OH*OW == 1)            */
 
 /* One Bayesian layer of a fused chain: the layer forward + KL (as bbb_conv2d_forward /

@@ -195,8 +195,8 @@ int bbb_layer_forward_fused(const bbb_layer_desc* d, const void* x, const void* 
     if (pool && ((g.OH | g.OW) & 1)) return fail(BBB_E_UNSUPPORTED, "fused pool needs even output height/width");
     const size_t need = bbb_workspace_bytes(d);
     if (!ws || ws_bytes < need) return fail(BBB_E_WORKSPACE, "workspace too small for the fused path: need %zu bytes", need);
-    if (out_layout == BBB_LAYOUT_PACKED_BF16 && (out_pitch % 8 || out_pitch < (pool ? g.OHW / 4 : g.OHW) * g.N))
-        return fail(BBB_E_INVALID, "bad out_pitch %d", out_pitch);
+    if (out_layout == BBB_LAYOUT_PACKED_BF16 && (g.N % 64 || out_pitch != (pool ? g.OHW / 4 : g.OHW) * g.N))
+        return fail(BBB_E_INVALID, "tiled packed output needs Cout %% 64 == 0 and out_pitch == pixels*Cout (got %d)", out_pitch);
     cudaStream_t st = (cudaStream_t)stream;
     const int out_mode = out_layout == BBB_LAYOUT_PACKED_BF16 ? 0 : (out_layout == BBB_LAYOUT_ROWMAJOR_F32 ? 1 : 2);
     int nl = 0;
@@ -218,7 +218,7 @@ int bbb_layer_forward_fused(const bbb_layer_desc* d, const void* x, const void* 
         if (e != cudaSuccess) return cuda_fail(e, "fused gather launch");
     } else if (in_layout == BBB_LAYOUT_PACKED_BF16) {
         if (!bbb::fused_supported(g, pool)) return fail(BBB_E_UNSUPPORTED, "shape not supported by the fused tap-GEMM path");
-        if (in_pitch % 8 || in_pitch < g.HW * g.Cin) return fail(BBB_E_INVALID, "bad in_pitch %d", in_pitch);
+        if (in_pitch != g.HW * g.Cin) return fail(BBB_E_INVALID, "tiled packed input: in_pitch must be pixels*Cin (got %d)", in_pitch);
         if (prev_hw < 1 || g.Cin % prev_hw) return fail(BBB_E_INVALID, "bad prev_hw %d", prev_hw);
         bbb::FusedArgs a;
         a.g = g; a.variant = d->variant; a.sample = d->sample; a.has_bias = d->has_bias; a.act = d->epilogue_act;

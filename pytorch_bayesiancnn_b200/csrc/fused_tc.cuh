@@ -37,9 +37,11 @@ struct FusedArgs {
     __nv_bfloat16* wtiles; float* bias_ws;
     int planes, ng, n_cblk, n_kblk, taps;
     int prev_hw;                 // linear fed by a flattened HxW map: k' = pix*C + c  <->  ref k = c*HW + pix
+    const void* x; const void* x_sq;   // tiled packed input (and its square)
     void* y; void* y_sq;
-    int out_mode, out_pitch, pool, in_pitch;
+    int out_mode, out_pitch, pool, in_pitch;   // pitches = F (columns) of the tiled packed matrices
     long long* trace;            // debug: per-CTA clock64 checkpoints (nullptr in production)
+    int dbg_mma_j;               // debug: K-steps issued per stage (4 in production)
 };
 
 __host__ __device__ inline size_t fused_wtile_elems(const FusedArgs& a) { return (size_t)a.planes * a.ng * 64; }
@@ -168,10 +170,14 @@ __device__ __forceinline__ float4 act_noise4(const NoiseKey& k, int b, int pix, 
     return z;
 }
 
+// Thread roles (416 threads): warps 0-7 epilogue (two groups of four; group h owns half of the tile's 64
+// columns; warps w and w+4 read the same TMEM lanes), warp 8 MMA issuer, warps 9-12 TMA producers (one
+// elected thread each; the copies of a stage are dealt round-robin so their ~100-cycle issue costs overlap).
+constexpr int TAP_THREADS = 416, TAP_NPROD = 4;
+
 template <int VARIANT>
-__global__ void __launch_bounds__(192, 1)
-tap_gemm_kernel(const FusedArgs p, const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a2,
-                const int stages) {
+__global__ void __launch_bounds__(TAP_THREADS, 1)
+tap_gemm_kernel(const FusedArgs p, const int stages) {
     extern __shared__ uint8_t smem_raw[];
     const Geom& g = p.g;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -186,7 +192,6 @@ tap_gemm_kernel(const FusedArgs p, const __grid_constant__ CUtensorMap tm_a, con
     const uint32_t tiles_off = 1024u;
     const uint32_t stage_bytes = (uint32_t)planes * (TC_A_BYTES + TC_B_BYTES);
     const uint32_t a2_off = TC_A_BYTES, b_off = (uint32_t)planes * TC_A_BYTES;
-    const uint32_t sub_bytes = (uint32_t)planes * ng * 128;          // one weight sub-tile (all planes)
     float* ez = reinterpret_cast<float*>(sm + tiles_off + (size_t)stages * stage_bytes);   // [64][128] LRT noise
 
     // output tile -> (pixel set, cout block)
@@ -203,8 +208,11 @@ tap_gemm_kernel(const FusedArgs p, const __grid_constant__ CUtensorMap tm_a, con
         for (int q = 1; q < 4; ++q) { goh[q] = goh[0]; gow[q] = gow[0]; }
     }
 
-    long long* tr = p.trace ? p.trace + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+    // debug trace: 128 slots per CTA -- [0,8) phase checkpoints, [8,40) MMA thread: full[s] passed at step it,
+    // [48,88) producer 0: empty[s] passed at step it, [88,128) producer 0: step it issued
+    long long* tr = p.trace ? p.trace + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 128 : nullptr;
     if (tr && threadIdx.x == 0) tr[0] = clock64();
+    pdl_trigger();
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
             mbar_init(smem_u32(&ctl->full[s]), 1);
@@ -220,24 +228,35 @@ tap_gemm_kernel(const FusedArgs p, const __grid_constant__ CUtensorMap tm_a, con
         ctl->bvar[c] = p.bias_ws[p.n_cblk * ng + n];
     }
     const uint32_t tmem_cols = two ? 128u : 64u;
-    if (warp == 4) tmem_alloc(smem_u32(&ctl->tmem_base), tmem_cols);
+    if (warp == 8) tmem_alloc(smem_u32(&ctl->tmem_base), tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = ctl->tmem_base;
     if (tr && threadIdx.x == 0) tr[1] = clock64();
 
-    if (warp == 5) {
-        // ======================= TMA producer ===================================
-        if (lane == 0) {
+    if (warp >= 9) {
+        // ======================= TMA producers ==================================
+        // The WHOLE warp executes the loop and the mbarrier waits; only the copies are issued by one lane.
+        // (tools/pipe_probe.cu: a try_wait that blocks with a single active lane is woken ~750 cycles late --
+        //  apparently by a time-out poll -- while a fully converged warp is woken as soon as the phase flips.)
+        {
+            const int pid = warp - 9;
+            pdl_wait();                                  // A / A^2 are the previous layer's output
             int it = 0;
             const size_t sub_elems = (size_t)planes * ng * 64;
-            const uint32_t a_bytes = (uint32_t)planes * TC_A_BYTES;
+            const __nv_bfloat16* zero_tile = p.wtiles + (size_t)p.taps * p.n_cblk * p.n_kblk * sub_elems;
+            const uint32_t gbytes = (uint32_t)ng * 128;                 // one group, one plane
+            // Issuing a stage (try_wait + expect_tx + its bulk copies) costs a single thread ~700-900 cycles of
+            // dependent latency (tools/tma_probe.cu: ~350 cycles per expect_tx + cp.async.bulk pair) while the data
+            // lands ~250 cycles later.  So the STEPS are dealt round-robin to the producer threads: producer p
+            // issues steps p, p+4, ...; four issue chains run concurrently.
+            const int n_copies = planes + groups * planes;   // 0 = A, 1 = A^2 (LRT), then (group, plane) weight pieces
+            const uint32_t my_bytes = (uint32_t)planes * TC_A_BYTES + (uint32_t)(groups * planes) * gbytes;
 #pragma unroll 1
             for (int ipix = 0; ipix < g.HW; ++ipix) {
                 const int ih = ipix / g.W, iw = ipix - ih * g.W;
                 const __nv_bfloat16* src[4];
-                const __nv_bfloat16* zero_tile = p.wtiles + (size_t)p.taps * p.n_cblk * p.n_kblk * sub_elems;
                 bool any = false;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -246,30 +265,36 @@ tap_gemm_kernel(const FusedArgs p, const __grid_constant__ CUtensorMap tm_a, con
                     any |= tp >= 0;
                 }
                 if (!any) continue;
-                const uint32_t bytes = a_bytes + (uint32_t)groups * sub_bytes;
-                const int col0 = ipix * g.Cin;
+                // A tile of (row tile, column block): one contiguous 16 KB block of the tiled packed activation
+                const size_t a_tile0 = ((size_t)blockIdx.y * (p.in_pitch >> 6) + (size_t)ipix * p.n_kblk) * (128 * 64);
 #pragma unroll 1
                 for (int kb = 0; kb < p.n_kblk; ++kb, ++it) {
+                    if ((it & (TAP_NPROD - 1)) != pid) continue;
                     const int s = it % stages;
+                    __syncwarp();
                     mbar_wait(smem_u32(&ctl->empty[s]), ((uint32_t)(it / stages) & 1u) ^ 1u);
+                    if (tr && it < 40 && lane == 0) tr[48 + it] = clock64();
+                    if (lane == 0) {
                     const uint32_t bar = smem_u32(&ctl->full[s]);
-                    mbar_arrive_expect_tx(bar, bytes);
-                    if (tr && it == 0) tr[2] = clock64();
+                    mbar_arrive_expect_tx(bar, my_bytes);
                     const uint32_t st = base + tiles_off + (uint32_t)s * stage_bytes;
-                    tma_load_2d(st, &tm_a, col0 + kb * 64, m0, bar);
-                    if (two) tma_load_2d(st + a2_off, &tm_a2, col0 + kb * 64, m0, bar);
-                    // weight planes: [plane][group][ng rows x 128 B]  -> every plane is one 64-row SW128 tile
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        if (q >= groups) break;
-                        const __nv_bfloat16* sp = src[q] ? src[q] + (size_t)kb * sub_elems : zero_tile;
-                        bulk_g2s(st + b_off + q * (ng * 128), sp, ng * 128, bar);
-                        if (two) bulk_g2s(st + b_off + TC_B_BYTES + q * (ng * 128), sp + ng * 64, ng * 128, bar);
+#pragma unroll 1
+                    for (int c = 0; c < n_copies; ++c) {
+                        if (c == 0) bulk_g2s(st, reinterpret_cast<const __nv_bfloat16*>(p.x) + a_tile0 + (size_t)kb * (128 * 64), TC_A_BYTES, bar);
+                        else if (c == 1 && two) bulk_g2s(st + a2_off, reinterpret_cast<const __nv_bfloat16*>(p.x_sq) + a_tile0 + (size_t)kb * (128 * 64), TC_A_BYTES, bar);
+                        else {
+                            const int w = c - planes, q = w / planes, pl = w - q * planes;
+                            const __nv_bfloat16* sp = src[q] ? src[q] + (size_t)kb * sub_elems + (size_t)pl * ng * 64 : zero_tile;
+                            bulk_g2s(st + b_off + pl * TC_B_BYTES + q * gbytes, sp, gbytes, bar);
+                        }
                     }
+                    if (tr && it < 40) tr[88 + it] = clock64();
+                    }
+                    __syncwarp();                        // stay converged: the next blocking wait must be a whole-warp wait
                 }
             }
         }
-    } else if (warp == 4) {
+    } else if (warp == 8) {
         // ======================= MMA issuer =====================================
         const uint32_t idesc = make_idesc_bf16(TC_BM, 64);
         // descriptors are linear in the (address >> 4) field: build them once, add offsets per MMA
@@ -286,14 +311,17 @@ tap_gemm_kernel(const FusedArgs p, const __grid_constant__ CUtensorMap tm_a, con
 #pragma unroll 1
             for (int kb = 0; kb < p.n_kblk; ++kb, ++it) {
                 const int s = it % stages;
+                __syncwarp();                            // converged whole-warp wait (see the producer comment)
                 mbar_wait(smem_u32(&ctl->full[s]), (uint32_t)(it / stages) & 1u);
                 tc_fence_after();
                 if (tr && it == 0 && lane == 0) tr[3] = clock64();
+                if (tr && it < 32 && lane == 0) tr[8 + it] = clock64();
                 if (lane == 0) {
                     const uint32_t so = ((uint32_t)s * stage_bytes) >> 4;
                     const uint64_t da = dA0 + so, db = dB0 + so;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
+                        if (j >= p.dbg_mma_j) break;
                         umma_bf16(tmem, da + 2 * j, db + 2 * j, idesc, (it | j) ? 1u : 0u);
                         if (two) umma_bf16(tmem + 64u, da + (a2_off >> 4) + 2 * j, db + (TC_B_BYTES >> 4) + 2 * j, idesc, (it | j) ? 1u : 0u);
                     }
@@ -306,16 +334,18 @@ tap_gemm_kernel(const FusedArgs p, const __grid_constant__ CUtensorMap tm_a, con
         __syncwarp();
         tc_fence_before();
     } else {
-        // ======================= epilogue =======================================
-        const int t = threadIdx.x, b = m0 + t;
+        // ======================= epilogue (warps 0-7) ===========================
+        const int t = threadIdx.x & 127, h = threadIdx.x >> 7, b = m0 + t;
         const bool bvalid = b < g.B;
         const bool philox = two && !p.eps_a;
+        // column c of the tile belongs to group h iff own(c): pool: channel (c & 15) >> 3 == h, else c >> 5 == h
         // (1) while the main loop runs: draw this row's LRT noise into smem (column-major, conflict free)
         if (philox && bvalid) {
             const NoiseKey nkey = effective_key(p.key, p.stream_base);
 #pragma unroll 1
             for (int c4 = 0; c4 < 16; ++c4) {
                 const int c = c4 * 4;
+                if ((p.pool ? ((c & 15) >> 3) : (c >> 5)) != h) continue;
                 const int q = p.pool ? (c >> 4) : 0;
                 const int n = p.pool ? (cb * 16 + (c & 15)) : (cb * 64 + c);
                 float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -324,7 +354,7 @@ tap_gemm_kernel(const FusedArgs p, const __grid_constant__ CUtensorMap tm_a, con
                 ez[(c + 2) * 128 + t] = z.z; ez[(c + 3) * 128 + t] = z.w;
             }
         }
-        bool any_mma = false;          // did the schedule of warp 4 contain at least one step?
+        bool any_mma = false;          // did the schedule of warp 8 contain at least one step?
 #pragma unroll 1
         for (int ipix = 0; ipix < g.HW && !any_mma; ++ipix) {
             const int ih = ipix / g.W, iw = ipix - ih * g.W;
@@ -333,15 +363,16 @@ tap_gemm_kernel(const FusedArgs p, const __grid_constant__ CUtensorMap tm_a, con
                 if (q < groups && tap_of(g, goh[q], gow[q], ih, iw) >= 0) any_mma = true;
         }
         // (2) accumulator ready
+        pdl_wait();                                      // our output buffers may still be read by the previous step's consumer
         mbar_wait(smem_u32(&ctl->accum), 0u);
         tc_fence_after();
         if (tr && threadIdx.x == 0) tr[5] = clock64();
-        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+        const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         const int ohw_out = p.pool ? (g.OHW >> 2) : g.OHW;
         const int n_base = p.pool ? cb * 16 : cb * 64;
-        const int n_iter = p.pool ? 2 : 8;                 // groups of 8 output channels
+        const int i_begin = p.pool ? h : 4 * h, i_end = p.pool ? h + 1 : 4 * h + 4;   // groups of 8 output channels
 #pragma unroll 1
-        for (int i8 = 0; i8 < n_iter; ++i8) {
+        for (int i8 = i_begin; i8 < i_end; ++i8) {
             float r[8];
             if (p.pool) {
 #pragma unroll
@@ -389,8 +420,8 @@ tap_gemm_kernel(const FusedArgs p, const __grid_constant__ CUtensorMap tm_a, con
             const int n0 = n_base + i8 * 8;
 #pragma unroll
             for (int u = 0; u < 8; ++u) r[u] = fast_act(r[u], p.act);       // act is monotone: act(max) == max(act)
-            if (p.out_mode == OUT_PACKED_BF16 && n0 + 8 <= g.N) {
-                const size_t off = (size_t)b * p.out_pitch + (size_t)pset * g.N + n0;
+            if (p.out_mode == OUT_PACKED_BF16) {          // tiled packed (N % 64 == 0 guaranteed by the host)
+                const size_t off = tiled_chunk_offset(b, pset * g.N + n0, p.out_pitch >> 6);
                 *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) + off) =
                     make_uint4(pack_bf16(r[0], r[1]), pack_bf16(r[2], r[3]), pack_bf16(r[4], r[5]), pack_bf16(r[6], r[7]));
                 if (p.y_sq)
@@ -402,11 +433,7 @@ tap_gemm_kernel(const FusedArgs p, const __grid_constant__ CUtensorMap tm_a, con
                 for (int u = 0; u < 8; ++u) {
                     const int n = n0 + u;
                     if (n >= g.N) break;
-                    if (p.out_mode == OUT_PACKED_BF16) {
-                        const size_t o = (size_t)b * p.out_pitch + (size_t)pset * g.N + n;
-                        reinterpret_cast<__nv_bfloat16*>(p.y)[o] = __float2bfloat16_rn(r[u]);
-                        if (p.y_sq) reinterpret_cast<__nv_bfloat16*>(p.y_sq)[o] = __float2bfloat16_rn(r[u] * r[u]);
-                    } else if (p.out_mode == OUT_ROWMAJOR_F32) {
+                    if (p.out_mode == OUT_ROWMAJOR_F32) {
                         reinterpret_cast<float*>(p.y)[((size_t)b * ohw_out + pset) * g.N + n] = r[u];
                     } else {
                         reinterpret_cast<float*>(p.y)[((size_t)b * g.N + n) * ohw_out + pset] = r[u];
@@ -419,8 +446,8 @@ tap_gemm_kernel(const FusedArgs p, const __grid_constant__ CUtensorMap tm_a, con
     }
     __syncthreads();
     tc_fence_after();
-    if (warp == 4) tmem_dealloc(tmem, tmem_cols);
-    if (tr && threadIdx.x == 128) tr[7] = clock64();
+    if (warp == 8) tmem_dealloc(tmem, tmem_cols);
+    if (tr && threadIdx.x == 256) tr[7] = clock64();
 }
 
 // ------------------------------------------------------------- host side
@@ -455,7 +482,7 @@ inline bool fused_supported(const Geom& g, int pool) {
     if (g.DH != 1 || g.DW != 1) return false;
     if (g.HW > 64) return false;                       // "small map" regime
     if (pool && ((g.OH & 1) || (g.OW & 1))) return false;
-    if (g.Cin % 8) return false;                       // TMA: 16-byte aligned column offsets per pixel
+    if (g.Cin % 64) return false;                      // tiled packed input: whole 64-column blocks per pixel
     return true;
 }
 
@@ -469,14 +496,8 @@ inline cudaError_t launch_fused(FusedArgs a, const void* x, const void* x_sq, cu
     a.n_kblk = (g.Cin + 63) / 64;
     a.taps = g.KHW;
     const bool lrt = a.variant == BBB_VARIANT_LRT;
-    CUtensorMap tma, tma2;
-    if (!do_gemm) { memset(&tma, 0, sizeof(tma)); tma2 = tma; }
-    else if (!make_act_tmap(&tma, x, g.B, g.HW * g.Cin, a.in_pitch)) { *why = "cuTensorMapEncodeTiled failed (A)"; return cudaErrorInvalidValue; }
-    if (!do_gemm) {
-    } else if (a.planes == 2) {
-        if (!x_sq) { *why = "LRT fused layer needs the squared activation"; return cudaErrorInvalidValue; }
-        if (!make_act_tmap(&tma2, x_sq, g.B, g.HW * g.Cin, a.in_pitch)) { *why = "cuTensorMapEncodeTiled failed (A^2)"; return cudaErrorInvalidValue; }
-    } else tma2 = tma;
+    a.x = x; a.x_sq = x_sq;
+    if (do_gemm && a.planes == 2 && !x_sq) { *why = "LRT fused layer needs the squared activation"; return cudaErrorInvalidValue; }
     if (do_prep) {
         const long items = (long)a.taps * a.n_cblk * a.n_kblk * a.ng * 8;
         int grid = (int)((items + 255) / 256);
@@ -489,7 +510,10 @@ inline cudaError_t launch_fused(FusedArgs a, const void* x, const void* x_sq, cu
         *n_launch += 1;
     }
     if (!do_gemm) return cudaSuccess;
-    const int stages = 4;                                            // 96 KB (1 plane) / 192 KB (2 planes)
+    a.dbg_mma_j = 4;
+    if (const char* e = getenv("BBB_B200_DBG_MMAJ")) a.dbg_mma_j = atoi(e);
+    int stages = 4;                                                  // 96 KB (1 plane) / 192 KB (2 planes)
+    if (const char* e = getenv("BBB_B200_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= 4) stages = v; }   // experiment knob
     const size_t smem = 2048 + (size_t)stages * tc_stage_bytes(a.planes) + (a.planes == 2 ? 64 * 128 * 4 : 0);   // + LRT noise tile
     const int psets = a.pool ? (g.OH / 2) * (g.OW / 2) : g.OHW;
     dim3 grid(psets * a.n_cblk, (g.B + TC_BM - 1) / TC_BM);
@@ -497,11 +521,13 @@ inline cudaError_t launch_fused(FusedArgs a, const void* x, const void* x_sq, cu
     if (lrt) {
         e = cudaFuncSetAttribute(tap_gemm_kernel<BBB_VARIANT_LRT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        tap_gemm_kernel<BBB_VARIANT_LRT><<<grid, 192, smem, st>>>(a, tma, tma2, stages);
+        e = launch_pdl(tap_gemm_kernel<BBB_VARIANT_LRT>, grid, dim3(TAP_THREADS), smem, st, a, stages);
+        if (e != cudaSuccess) return e;
     } else {
         e = cudaFuncSetAttribute(tap_gemm_kernel<BBB_VARIANT_BBB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        tap_gemm_kernel<BBB_VARIANT_BBB><<<grid, 192, smem, st>>>(a, tma, tma2, stages);
+        e = launch_pdl(tap_gemm_kernel<BBB_VARIANT_BBB>, grid, dim3(TAP_THREADS), smem, st, a, stages);
+        if (e != cudaSuccess) return e;
     }
     e = cudaGetLastError();
     if (e == cudaSuccess) *n_launch += 1;

@@ -28,6 +28,7 @@
 // BBB_LRT/BBBConv.py:62-87, BBB_LRT/BBBLinear.py:56-79, metrics.py:27-29.
 #pragma once
 #include <cuda_bf16.h>
+#include <cstdlib>
 #include "common.cuh"
 #include "fwd_simt.cuh"   // apply_act
 
@@ -144,6 +145,30 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Programmatic dependent launch: a kernel launched with the programmatic-serialization attribute may start
+// while its predecessor in the stream is still running; it must execute pdl_wait() before touching anything
+// the predecessor writes.  pdl_trigger() lets the successor's CTAs start filling idle SMs early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+    static int v = -1;
+    // opt-in: measured no gain inside the captured graph (round 1)
+    if (v < 0) { const char* e = getenv("BBB_B200_PDL"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+// <<<grid, block, smem, stream>>> with the programmatic-stream-serialization attribute when enabled
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // K-major, SWIZZLE_NONE ("interleave") shared-memory matrix descriptor (sm_100):
 //   [0,14)  start address >> 4        [16,30) leading-dim byte offset >> 4 (stride between
 //   the two 16-byte K chunks of one MMA)  [32,46) stride-dim byte offset >> 4 (stride between
@@ -164,6 +189,16 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 
 enum { OUT_PACKED_BF16 = 0, OUT_ROWMAJOR_F32 = 1, OUT_NCHW_F32 = 2 };
+
+// "Tiled packed" inter-layer activation: the [B, F] bf16 matrix (F = pixels x channels, F % 64 == 0) is stored as
+// [B/128 row tiles][F/64 column blocks][128 rows x 128 B], every 16 KB block already in the K-major SWIZZLE_128B
+// smem image -- the consumer stages an A tile with ONE 16 KB cp.async.bulk instead of a 128-row tensor-map box
+// (measured: the strided box costs ~900 cycles per stage regardless of bytes, stages or CTA count).
+// Offset (in elements) of the 8-element chunk holding columns [col, col+8) of row b:
+__device__ __forceinline__ size_t tiled_chunk_offset(int b, int col, int kb_total) {
+    const int r = b & 127, kb = col >> 6, ch = (col & 63) >> 3;
+    return ((size_t)(b >> 7) * kb_total + kb) * (128 * 64) + (size_t)r * 64 + (size_t)((ch ^ (r & 7)) << 3);
+}
 
 // Epilogue math of the bf16 path: MUFU-based, a handful of instructions (the exact versions in
 // fwd_simt.cuh cost ~100 instructions per value and the epilogue warps run at IPC ~0.25).
@@ -332,8 +367,9 @@ gemm_tc_kernel(const TcArgs p, const int stages) {
     const int chw = g.Cin * g.HW;
     const int img0 = m0 / g.OHW;
 
-    long long* tr = p.trace ? p.trace + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+    long long* tr = p.trace ? p.trace + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 128 : nullptr;
     if (tr && threadIdx.x == 0) tr[0] = clock64();
+    pdl_trigger();
     // ---- one-time setup ------------------------------------------------------
     for (int k = threadIdx.x; k < kpad; k += blockDim.x) {
         int2 e;
@@ -345,6 +381,7 @@ gemm_tc_kernel(const TcArgs p, const int stages) {
         } else { e.x = 0; e.y = 0x7fff7fff; }
         ktab[k] = e;
     }
+    pdl_wait();                                         // everything below reads/writes tensors other kernels touch
     if (p.stage_x) {
         // the tile's input images, loaded once and coalesced; the im2col gather then reads shared memory
         // (LDS latency ~30 cycles) instead of issuing 64 dependent-latency global loads per thread and k-block
@@ -484,8 +521,8 @@ gemm_tc_kernel(const TcArgs p, const int stages) {
                 am[j] = fast_act(val, p.act);           // act is monotone: act(max) == max(act)
             }
             if (!writer) continue;
-            if (p.out_mode == OUT_PACKED_BF16 && nb + 8 <= g.N) {
-                const size_t off = (size_t)bimg * p.out_pitch + (size_t)opix * g.N + nb;
+            if (p.out_mode == OUT_PACKED_BF16) {          // tiled packed (N % 64 == 0 guaranteed by the host)
+                const size_t off = tiled_chunk_offset(bimg, opix * g.N + nb, p.out_pitch >> 6);
                 *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) + off) =
                     make_uint4(pack_bf16(am[0], am[1]), pack_bf16(am[2], am[3]), pack_bf16(am[4], am[5]), pack_bf16(am[6], am[7]));
                 if (p.y_sq)
@@ -497,13 +534,7 @@ gemm_tc_kernel(const TcArgs p, const int stages) {
                 for (int j = 0; j < 8; ++j) {
                     const int n = nb + j;
                     if (n >= g.N) continue;
-                    if (p.out_mode == OUT_PACKED_BF16) {
-                        const size_t o = (size_t)bimg * p.out_pitch + (size_t)opix * g.N + n;
-                        reinterpret_cast<__nv_bfloat16*>(p.y)[o] = __float2bfloat16_rn(am[j]);
-                        if (p.y_sq) reinterpret_cast<__nv_bfloat16*>(p.y_sq)[o] = __float2bfloat16_rn(am[j] * am[j]);
-                    } else {
-                        reinterpret_cast<float*>(p.y)[((size_t)bimg * g.N + n) * ohw_out + opix] = am[j];
-                    }
+                    reinterpret_cast<float*>(p.y)[((size_t)bimg * g.N + n) * ohw_out + opix] = am[j];
                 }
             }
         }
@@ -515,6 +546,7 @@ gemm_tc_kernel(const TcArgs p, const int stages) {
         for (int kb = 0; kb < p.k_blocks; ++kb) {
             const int s = kb % stages;
             const uint32_t ph = (uint32_t)(kb / stages) & 1u;
+            __syncwarp();
             mbar_wait(smem_u32(&ctl->full[s]), ph);
             tc_fence_after();
             if (lane == 0) {
@@ -538,16 +570,21 @@ gemm_tc_kernel(const TcArgs p, const int stages) {
         tc_fence_before();
     } else {
         // ================= weight-tile TMA ======================================
-        if (lane == 0) {
+        // whole warp waits (a blocking try_wait with one active lane is woken ~750 cycles late), lane 0 issues
+        {
             const uint32_t bytes = (uint32_t)planes * TC_B_BYTES;
             const __nv_bfloat16* src0 = p.wtiles + (size_t)n_tile * p.k_blocks * planes * TC_TILE_ELEMS;
             for (int kb = 0; kb < p.k_blocks; ++kb) {
                 const int s = kb % stages;
                 const uint32_t ph = (uint32_t)(kb / stages) & 1u;
+                __syncwarp();
                 mbar_wait(smem_u32(&ctl->empty[s]), ph ^ 1u);
-                const uint32_t bar = smem_u32(&ctl->full[s]);
-                mbar_arrive_expect_tx(bar, bytes);
-                bulk_g2s(base + tiles_off + (uint32_t)s * stage_bytes + b_off, src0 + (size_t)kb * planes * TC_TILE_ELEMS, bytes, bar);
+                if (lane == 0) {
+                    const uint32_t bar = smem_u32(&ctl->full[s]);
+                    mbar_arrive_expect_tx(bar, bytes);
+                    bulk_g2s(base + tiles_off + (uint32_t)s * stage_bytes + b_off, src0 + (size_t)kb * planes * TC_TILE_ELEMS, bytes, bar);
+                }
+                __syncwarp();
             }
         }
     }
@@ -589,11 +626,13 @@ inline cudaError_t launch_fwd_tc(TcArgs a, cudaStream_t st, int n_sm, int* n_lau
     if (lrt) {
         e = cudaFuncSetAttribute(gemm_tc_kernel<BBB_VARIANT_LRT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        gemm_tc_kernel<BBB_VARIANT_LRT><<<grid, 320, smem, st>>>(a, stages);
+        e = launch_pdl(gemm_tc_kernel<BBB_VARIANT_LRT>, grid, dim3(320), smem, st, a, stages);
+        if (e != cudaSuccess) return e;
     } else {
         e = cudaFuncSetAttribute(gemm_tc_kernel<BBB_VARIANT_BBB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        gemm_tc_kernel<BBB_VARIANT_BBB><<<grid, 320, smem, st>>>(a, stages);
+        e = launch_pdl(gemm_tc_kernel<BBB_VARIANT_BBB>, grid, dim3(320), smem, st, a, stages);
+        if (e != cudaSuccess) return e;
     }
     (void)n_sm;
     e = cudaGetLastError();

@@ -77,7 +77,7 @@ def plan(children, x_shape):
             oh, ow = (h + 2 * ph - kh) // sh + 1, (w + 2 * pw - kw) // sw + 1
             if oh < 1 or ow < 1:
                 return None
-            if lay == "packed" and (h * w > 64 or c % 8):
+            if lay == "packed" and (h * w > 64 or c % 64):
                 return None
             st.prev_hw = 1
             st.in_shape = (c, h, w)
@@ -109,6 +109,8 @@ def plan(children, x_shape):
     last.out_layout = L.LAYOUT_ROWMAJOR_F32 if last.out_chw[1] * last.out_chw[2] == 1 else L.LAYOUT_NCHW_F32
     for st in steps[:-1]:
         st.out_layout = L.LAYOUT_PACKED_BF16
+        if st.out_chw[0] % 64:                  # tiled packed format: whole 64-channel blocks per pixel
+            return None
     return steps
 
 
@@ -180,14 +182,14 @@ def run_step(st, nxt, cur, cur_sq, cur_pitch, kl=None, noise=None, phase=0):
     lib = L.lib()
     m = st.layer
     dev = m.W_mu.device
-    B = st.batch if cur is None else cur.shape[0]
+    B = st.batch                                    # (packed inputs carry rows padded to the 128-row tile)
     if True:
         lrt = m._variant == L.VARIANT_LRT
         stoch = True                                     # ModuleWrapper calls children with sample=True
         cin, h, w = st.in_shape
         d = L.LayerDesc()
         d.batch, d.in_channels, d.in_h, d.in_w = B, cin, h, w
-        in_pitch = cur_pitch if st.in_layout == L.LAYOUT_NCHW_F32 else (cin * h * w + 7) // 8 * 8
+        in_pitch = cur_pitch if st.in_layout == L.LAYOUT_NCHW_F32 else cin * h * w
         if st.linear:
             d.out_channels, d.kernel_h, d.kernel_w = m.out_features, 1, 1
             d.stride_h = d.stride_w = d.dil_h = d.dil_w = 1
@@ -205,10 +207,10 @@ def run_step(st, nxt, cur, cur_sq, cur_pitch, kl=None, noise=None, phase=0):
         d.prior_mu, d.prior_sigma = float(m.prior_mu), float(m.prior_sigma)
         cout, oh, ow = st.out_chw
         if phase == L.FUSED_PREP_ONLY:
-            pitch, y, y_sq = (cout * oh * ow + 7) // 8 * 8 if st.out_layout == L.LAYOUT_PACKED_BF16 else 0, None, None
+            pitch, y, y_sq = cout * oh * ow if st.out_layout == L.LAYOUT_PACKED_BF16 else 0, None, None
         elif st.out_layout == L.LAYOUT_PACKED_BF16:
-            pitch = (cout * oh * ow + 7) // 8 * 8
-            y = torch.empty(B, pitch, dtype=torch.bfloat16, device=dev)
+            pitch = cout * oh * ow                   # tiled packed: [ceil(B/128)][F/64][128 x 64] bf16
+            y = torch.empty((B + 127) // 128 * 128, pitch, dtype=torch.bfloat16, device=dev)
             y_sq = torch.empty_like(y) if (nxt is not None and nxt._variant == L.VARIANT_LRT) else None
         elif st.out_layout == L.LAYOUT_ROWMAJOR_F32:
             pitch, y, y_sq = 0, torch.empty(B, cout, dtype=torch.float32, device=dev), None

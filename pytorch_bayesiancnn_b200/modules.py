@@ -59,7 +59,7 @@ class ModuleWrapper(nn.Module):
             return None                                    # the fused chain is forward-only
         from . import fused
         plans = self.__dict__.setdefault("_fused_plans", {})
-        key = tuple(x.shape[1:])
+        key = tuple(x.shape)
         if key not in plans:
             kids = list(self.children())
             plans[key] = fused.plan(kids, tuple(x.shape)) if kids else None

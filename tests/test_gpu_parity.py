@@ -357,7 +357,7 @@ def test_fused_chain_vs_oracle_external_eps(dev):
             ref, refkl = O.net_forward("alexnet", params, x, eps, variant, act, 0.0, 0.1, classes)
             with torch.no_grad(), bbb.external_eps(eps):
                 logits, kl = net(x.to(dev))
-            assert net._fused_plans[(3, 32, 32)] is not None          # it really took the fused path
+            assert net._fused_plans[(batch, 3, 32, 32)] is not None   # it really took the fused path
             e = scale_err(logits, ref)
             print("fused", variant, batch, classes, act, "scale err", e)
             assert e < 2 * BF16_TOL, (variant, batch, e)

@@ -19,7 +19,7 @@ lib = L.lib()
 lib._handle  # noqa
 fn = C.CDLL(L.LIB_PATH).bbb_debug_set_trace
 fn.argtypes = [C.c_void_p]
-trace = torch.zeros(4096 * 8, dtype=torch.int64, device=dev)
+trace = torch.zeros(4096 * 128, dtype=torch.int64, device=dev)
 names = ["entry", "setup", "tma0|kb0", "full0|prod_end", "lastmma", "accum", "epi_end", "exit"]
 with torch.no_grad():
     for rep in range(3):
@@ -32,10 +32,17 @@ with torch.no_grad():
             cur, sq, pitch = fused.run_step(st, nxt, cur, sq, pitch)
             torch.cuda.synchronize()
             if rep == 2:
-                t = trace.view(-1, 8).cpu()
+                t = trace.view(-1, 128).cpu()
                 t = t[t[:, 0] != 0]
                 rel = (t - t[:, :1]).double()
                 print(f"layer {i}: {t.shape[0]} CTAs; mean cycles since entry:",
                       {n: int(rel[:, k].mean()) for k, n in enumerate(names)},
                       "max exit", int(rel[:, 7].max()))
+                if i > 0:
+                    one = rel[0]
+                    nst = int((t[0, 8:40] != 0).sum())
+                    print("   CTA0 per step: mma_full", [int(one[8 + k]) for k in range(nst)])
+                    print("   CTA0 per step: tma_empty", [int(one[48 + k]) for k in range(nst)])
+                    print("   CTA0 per step: tma_issued", [int(one[88 + k]) for k in range(nst)])
+                    print("   CTA0 issue->full latency", [int(one[8 + k] - one[88 + k]) for k in range(nst)])
     fn(None)
