@@ -42,6 +42,7 @@ struct FusedArgs {
     int out_mode, out_pitch, pool, in_pitch;   // pitches = F (columns) of the tiled packed matrices
     long long* trace;            // debug: per-CTA clock64 checkpoints (nullptr in production)
     int dbg_mma_j;               // debug: K-steps issued per stage (4 in production)
+    int dbg_mode;                // debug: bit0 skip weight copies, bit1 skip A copies, bit2 free stages with a plain arrive
 };
 
 __host__ __device__ inline size_t fused_wtile_elems(const FusedArgs& a) { return (size_t)a.planes * a.ng * 64; }
@@ -139,10 +140,18 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
            (1ull << 46) | (2ull << 61);
 }
 
+constexpr int TAP_MAX_ITEMS = 64;       // live (input pixel, 64-channel block) pairs per tile (control block must stay < 2 KB)
+constexpr int TAP_UNITS = 2;            // K blocks handled per pipeline step (one mbarrier phase)
+static_assert(true, "");
 struct FusedSmem {
     unsigned long long full[4], empty[4], accum;
-    uint32_t tmem_base, pad;
+    uint32_t tmem_base, n_items;
     float bias[64], bvar[64];       // this tile's 64 output columns
+    // K-loop schedule, built once per CTA: x = ipix | kb << 16, y = the four column groups' taps (0xFF = outside the
+    // kernel window -> zero sub-tile).  A pipeline step covers TAP_UNITS consecutive items: the fixed cost of a stage
+    // hand-off (~500-900 cycles measured: barrier round trip + TMA issue + first-MMA start-up) is paid per STEP.
+    int2 items[TAP_MAX_ITEMS];
+    int taps_px[64];                // per input pixel: packed taps (staging for the schedule build)
 };
 
 // tap linking output pixel (oh,ow) with input pixel (ih,iw); -1 if outside the kernel window
@@ -189,8 +198,9 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (base - raw);
     FusedSmem* ctl = reinterpret_cast<FusedSmem*>(sm);
-    const uint32_t tiles_off = 1024u;
-    const uint32_t stage_bytes = (uint32_t)planes * (TC_A_BYTES + TC_B_BYTES);
+    const uint32_t tiles_off = 2048u;
+    const uint32_t unit_bytes = (uint32_t)planes * (TC_A_BYTES + TC_B_BYTES);   // one K block: [A][A^2][B planes]
+    const uint32_t stage_bytes = TAP_UNITS * unit_bytes;
     const uint32_t a2_off = TC_A_BYTES, b_off = (uint32_t)planes * TC_A_BYTES;
     float* ez = reinterpret_cast<float*>(sm + tiles_off + (size_t)stages * stage_bytes);   // [64][128] LRT noise
 
@@ -221,6 +231,27 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
         mbar_init(smem_u32(&ctl->accum), 1);
         fence_barrier_init();
     }
+    // K-loop schedule: one thread per input pixel works out the taps (integer divisions), thread 64 compacts
+    if (threadIdx.x >= 128 && threadIdx.x < 128 + g.HW) {
+        const int ipix = threadIdx.x - 128;
+        const int ih = ipix / g.W, iw = ipix - ih * g.W;
+        uint32_t taps = 0;
+        for (int q = 0; q < 4; ++q) {
+            const int tp = (q < groups) ? tap_of(g, goh[q], gow[q], ih, iw) : -1;
+            taps |= (uint32_t)(tp >= 0 ? tp : 0xFF) << (8 * q);
+        }
+        ctl->taps_px[ipix] = (int)taps;
+    }
+    __syncthreads();
+    if (threadIdx.x == 64) {
+        int n = 0;
+        for (int ipix = 0; ipix < g.HW; ++ipix) {
+            const int taps = ctl->taps_px[ipix];
+            if ((uint32_t)taps == 0xFFFFFFFFu) continue;
+            for (int kb = 0; kb < p.n_kblk; ++kb) ctl->items[n++] = make_int2(ipix | (kb << 16), taps);
+        }
+        ctl->n_items = (uint32_t)n;
+    }
     if (threadIdx.x < 64) {                              // bias / bias variance of this tile's columns
         const int c = threadIdx.x;
         const int n = p.pool ? (cb * 16 + (c & 15)) : (cb * 64 + c);
@@ -235,64 +266,62 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
     const uint32_t tmem = ctl->tmem_base;
     if (tr && threadIdx.x == 0) tr[1] = clock64();
 
+    const int n_items = (int)ctl->n_items;
+    const int n_steps = (n_items + TAP_UNITS - 1) / TAP_UNITS;
+
     if (warp >= 9) {
         // ======================= TMA producers ==================================
         // The WHOLE warp executes the loop and the mbarrier waits; only the copies are issued by one lane.
         // (tools/pipe_probe.cu: a try_wait that blocks with a single active lane is woken ~750 cycles late --
         //  apparently by a time-out poll -- while a fully converged warp is woken as soon as the phase flips.)
-        {
-            const int pid = warp - 9;
-            pdl_wait();                                  // A / A^2 are the previous layer's output
-            int it = 0;
-            const size_t sub_elems = (size_t)planes * ng * 64;
-            const __nv_bfloat16* zero_tile = p.wtiles + (size_t)p.taps * p.n_cblk * p.n_kblk * sub_elems;
-            const uint32_t gbytes = (uint32_t)ng * 128;                 // one group, one plane
-            // Issuing a stage (try_wait + expect_tx + its bulk copies) costs a single thread ~700-900 cycles of
-            // dependent latency (tools/tma_probe.cu: ~350 cycles per expect_tx + cp.async.bulk pair) while the data
-            // lands ~250 cycles later.  So the STEPS are dealt round-robin to the producer threads: producer p
-            // issues steps p, p+4, ...; four issue chains run concurrently.
-            const int n_copies = planes + groups * planes;   // 0 = A, 1 = A^2 (LRT), then (group, plane) weight pieces
-            const uint32_t my_bytes = (uint32_t)planes * TC_A_BYTES + (uint32_t)(groups * planes) * gbytes;
+        // Issuing a stage costs one thread several hundred cycles of dependent latency (tools/tma_probe.cu: ~350
+        // cycles per expect_tx + cp.async.bulk pair) while the data lands ~250 cycles later, so the STEPS are dealt
+        // round-robin to the four producer warps: four issue chains run concurrently.
+        // A producer must see EVERY phase of the stage it fills (parity waits alias after two phases), so at most
+        // `stages` producers take part and producer p owns stage p (mod nprod).
+        const int pid = warp - 9;
+        const int nprod = min(TAP_NPROD, stages);
+        pdl_wait();                                      // A / A^2 are the previous layer's output
+        const size_t sub_elems = (size_t)planes * ng * 64;
+        const __nv_bfloat16* zero_tile = p.wtiles + (size_t)p.taps * p.n_cblk * p.n_kblk * sub_elems;
+        const uint32_t gbytes = (uint32_t)ng * 128;                     // one group, one plane
+        const uint32_t unit_tx = ((p.dbg_mode & 2) ? 0u : (uint32_t)planes * TC_A_BYTES) +
+                                 ((p.dbg_mode & 1) ? 0u : (uint32_t)(groups * planes) * gbytes);
+        const size_t a_row0 = (size_t)blockIdx.y * (p.in_pitch >> 6);   // first 16 KB block of this row tile
 #pragma unroll 1
-            for (int ipix = 0; ipix < g.HW; ++ipix) {
-                const int ih = ipix / g.W, iw = ipix - ih * g.W;
-                const __nv_bfloat16* src[4];
-                bool any = false;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int tp = (q < groups) ? tap_of(g, goh[q], gow[q], ih, iw) : -1;
-                    src[q] = tp >= 0 ? p.wtiles + (size_t)(tp * p.n_cblk + cb) * p.n_kblk * sub_elems : nullptr;
-                    any |= tp >= 0;
-                }
-                if (!any) continue;
-                // A tile of (row tile, column block): one contiguous 16 KB block of the tiled packed activation
-                const size_t a_tile0 = ((size_t)blockIdx.y * (p.in_pitch >> 6) + (size_t)ipix * p.n_kblk) * (128 * 64);
+        for (int it = pid; it < n_steps && pid < nprod; it += nprod) {
+            const int s = it % stages;
+            __syncwarp();
+            mbar_wait(smem_u32(&ctl->empty[s]), ((uint32_t)(it / stages) & 1u) ^ 1u);
+            if (tr && it < 40 && lane == 0) tr[48 + it] = clock64();
+            if (lane == 0) {
+                const int i0 = it * TAP_UNITS, nu = min(TAP_UNITS, n_items - i0);
+                const uint32_t bar = smem_u32(&ctl->full[s]);
+                mbar_arrive_expect_tx(bar, unit_tx * nu);
 #pragma unroll 1
-                for (int kb = 0; kb < p.n_kblk; ++kb, ++it) {
-                    if ((it & (TAP_NPROD - 1)) != pid) continue;
-                    const int s = it % stages;
-                    __syncwarp();
-                    mbar_wait(smem_u32(&ctl->empty[s]), ((uint32_t)(it / stages) & 1u) ^ 1u);
-                    if (tr && it < 40 && lane == 0) tr[48 + it] = clock64();
-                    if (lane == 0) {
-                    const uint32_t bar = smem_u32(&ctl->full[s]);
-                    mbar_arrive_expect_tx(bar, my_bytes);
-                    const uint32_t st = base + tiles_off + (uint32_t)s * stage_bytes;
+                for (int u = 0; u < nu; ++u) {
+                    const int2 item = ctl->items[i0 + u];
+                    const int ipix = item.x & 0xffff, kb = item.x >> 16;
+                    const uint32_t st = base + tiles_off + (uint32_t)s * stage_bytes + (uint32_t)u * unit_bytes;
+                    const size_t a_blk = (a_row0 + (size_t)ipix * p.n_kblk + kb) * (128 * 64);
+                    if (!(p.dbg_mode & 2)) {
+                        bulk_g2s(st, reinterpret_cast<const __nv_bfloat16*>(p.x) + a_blk, TC_A_BYTES, bar);
+                        if (two) bulk_g2s(st + a2_off, reinterpret_cast<const __nv_bfloat16*>(p.x_sq) + a_blk, TC_A_BYTES, bar);
+                    }
+                    if (!(p.dbg_mode & 1)) {
+                        // weight planes: [plane][group][ng rows x 128 B] -> every plane is one 64-row SW128 tile
 #pragma unroll 1
-                    for (int c = 0; c < n_copies; ++c) {
-                        if (c == 0) bulk_g2s(st, reinterpret_cast<const __nv_bfloat16*>(p.x) + a_tile0 + (size_t)kb * (128 * 64), TC_A_BYTES, bar);
-                        else if (c == 1 && two) bulk_g2s(st + a2_off, reinterpret_cast<const __nv_bfloat16*>(p.x_sq) + a_tile0 + (size_t)kb * (128 * 64), TC_A_BYTES, bar);
-                        else {
-                            const int w = c - planes, q = w / planes, pl = w - q * planes;
-                            const __nv_bfloat16* sp = src[q] ? src[q] + (size_t)kb * sub_elems + (size_t)pl * ng * 64 : zero_tile;
-                            bulk_g2s(st + b_off + pl * TC_B_BYTES + q * gbytes, sp, gbytes, bar);
+                        for (int q = 0; q < groups; ++q) {
+                            const int tp = (item.y >> (8 * q)) & 0xFF;
+                            const __nv_bfloat16* sp = tp != 0xFF ? p.wtiles + ((size_t)(tp * p.n_cblk + cb) * p.n_kblk + kb) * sub_elems : zero_tile;
+                            bulk_g2s(st + b_off + q * gbytes, sp, gbytes, bar);
+                            if (two) bulk_g2s(st + b_off + TC_B_BYTES + q * gbytes, tp != 0xFF ? sp + ng * 64 : zero_tile, gbytes, bar);
                         }
                     }
-                    if (tr && it < 40) tr[88 + it] = clock64();
-                    }
-                    __syncwarp();                        // stay converged: the next blocking wait must be a whole-warp wait
                 }
+                if (tr && it < 40) tr[88 + it] = clock64();
             }
+            __syncwarp();                                // stay converged: the next blocking wait must be a whole-warp wait
         }
     } else if (warp == 8) {
         // ======================= MMA issuer =====================================
@@ -300,35 +329,30 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
         // descriptors are linear in the (address >> 4) field: build them once, add offsets per MMA
         const uint64_t dA0 = make_smem_desc_sw128(base + tiles_off);
         const uint64_t dB0 = make_smem_desc_sw128(base + tiles_off + b_off);
-        int it = 0;
 #pragma unroll 1
-        for (int ipix = 0; ipix < g.HW; ++ipix) {
-            const int ih = ipix / g.W, iw = ipix - ih * g.W;
-            bool live = false;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) if (q < groups && tap_of(g, goh[q], gow[q], ih, iw) >= 0) live = true;
-            if (!live) continue;
+        for (int it = 0; it < n_steps; ++it) {
+            const int s = it % stages;
+            __syncwarp();                                // converged whole-warp wait (see the producer comment)
+            mbar_wait(smem_u32(&ctl->full[s]), (uint32_t)(it / stages) & 1u);
+            tc_fence_after();
+            if (tr && it == 0 && lane == 0) tr[3] = clock64();
+            if (tr && it < 32 && lane == 0) tr[8 + it] = clock64();
+            if (lane == 0) {
+                const int nu = min(TAP_UNITS, n_items - it * TAP_UNITS);
 #pragma unroll 1
-            for (int kb = 0; kb < p.n_kblk; ++kb, ++it) {
-                const int s = it % stages;
-                __syncwarp();                            // converged whole-warp wait (see the producer comment)
-                mbar_wait(smem_u32(&ctl->full[s]), (uint32_t)(it / stages) & 1u);
-                tc_fence_after();
-                if (tr && it == 0 && lane == 0) tr[3] = clock64();
-                if (tr && it < 32 && lane == 0) tr[8 + it] = clock64();
-                if (lane == 0) {
-                    const uint32_t so = ((uint32_t)s * stage_bytes) >> 4;
+                for (int u = 0; u < nu; ++u) {
+                    const uint32_t so = ((uint32_t)s * stage_bytes + (uint32_t)u * unit_bytes) >> 4;
                     const uint64_t da = dA0 + so, db = dB0 + so;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         if (j >= p.dbg_mma_j) break;
-                        umma_bf16(tmem, da + 2 * j, db + 2 * j, idesc, (it | j) ? 1u : 0u);
-                        if (two) umma_bf16(tmem + 64u, da + (a2_off >> 4) + 2 * j, db + (TC_B_BYTES >> 4) + 2 * j, idesc, (it | j) ? 1u : 0u);
+                        umma_bf16(tmem, da + 2 * j, db + 2 * j, idesc, (it | u | j) ? 1u : 0u);
+                        if (two) umma_bf16(tmem + 64u, da + (a2_off >> 4) + 2 * j, db + (TC_B_BYTES >> 4) + 2 * j, idesc, (it | u | j) ? 1u : 0u);
                     }
-                    umma_commit(smem_u32(&ctl->empty[s]));
                 }
-                __syncwarp();
+                if (p.dbg_mode & 4) mbar_arrive(smem_u32(&ctl->empty[s])); else umma_commit(smem_u32(&ctl->empty[s]));
             }
+            __syncwarp();
         }
         if (lane == 0) { umma_commit(smem_u32(&ctl->accum)); if (tr) tr[4] = clock64(); }
         __syncwarp();
@@ -354,14 +378,7 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
                 ez[(c + 2) * 128 + t] = z.z; ez[(c + 3) * 128 + t] = z.w;
             }
         }
-        bool any_mma = false;          // did the schedule of warp 8 contain at least one step?
-#pragma unroll 1
-        for (int ipix = 0; ipix < g.HW && !any_mma; ++ipix) {
-            const int ih = ipix / g.W, iw = ipix - ih * g.W;
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (q < groups && tap_of(g, goh[q], gow[q], ih, iw) >= 0) any_mma = true;
-        }
+        const bool any_mma = n_items > 0;  // did the schedule of warp 8 contain at least one step?
         // (2) accumulator ready
         pdl_wait();                                      // our output buffers may still be read by the previous step's consumer
         mbar_wait(smem_u32(&ctl->accum), 0u);
@@ -483,6 +500,7 @@ inline bool fused_supported(const Geom& g, int pool) {
     if (g.HW > 64) return false;                       // "small map" regime
     if (pool && ((g.OH & 1) || (g.OW & 1))) return false;
     if (g.Cin % 64) return false;                      // tiled packed input: whole 64-column blocks per pixel
+    if ((long)g.HW * (g.Cin / 64) > TAP_MAX_ITEMS) return false;
     return true;
 }
 
@@ -510,11 +528,12 @@ inline cudaError_t launch_fused(FusedArgs a, const void* x, const void* x_sq, cu
         *n_launch += 1;
     }
     if (!do_gemm) return cudaSuccess;
-    a.dbg_mma_j = 4;
+    a.dbg_mma_j = 4; a.dbg_mode = 0;
+    if (const char* e = getenv("BBB_B200_DBG_MODE")) a.dbg_mode = atoi(e);
     if (const char* e = getenv("BBB_B200_DBG_MMAJ")) a.dbg_mma_j = atoi(e);
-    int stages = 4;                                                  // 96 KB (1 plane) / 192 KB (2 planes)
-    if (const char* e = getenv("BBB_B200_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= 4) stages = v; }   // experiment knob
-    const size_t smem = 2048 + (size_t)stages * tc_stage_bytes(a.planes) + (a.planes == 2 ? 64 * 128 * 4 : 0);   // + LRT noise tile
+    int stages = a.planes == 2 ? 2 : 4;                              // stage = 2 K blocks: 48 KB (1 plane) / 96 KB (2 planes)
+    if (const char* e = getenv("BBB_B200_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= (a.planes == 2 ? 2 : 4)) stages = v; }   // experiment knob
+    const size_t smem = 1024 + 2048 + (size_t)stages * TAP_UNITS * tc_stage_bytes(a.planes) + (a.planes == 2 ? 64 * 128 * 4 : 0);   // align slack + control/schedule + ring + LRT noise tile
     const int psets = a.pool ? (g.OH / 2) * (g.OW / 2) : g.OHW;
     dim3 grid(psets * a.n_cblk, (g.B + TC_BM - 1) / TC_BM);
     cudaError_t e;

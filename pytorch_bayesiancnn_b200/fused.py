@@ -117,10 +117,10 @@ def plan(children, x_shape):
 _side_streams: dict = {}
 
 
-def _side_stream(dev):
-    st = _side_streams.get(dev.index)
+def _side_stream(dev, i=0):
+    st = _side_streams.get((dev.index, i))
     if st is None:
-        st = _side_streams[dev.index] = torch.cuda.Stream(device=dev)
+        st = _side_streams[(dev.index, i)] = torch.cuda.Stream(device=dev)
     return st
 
 
@@ -135,11 +135,14 @@ def run(steps, x: torch.Tensor, overlap_prep: bool = True):
     kls = torch.empty(len(steps), dtype=torch.float32, device=dev)
     noise = [_draw_noise(st, x.shape[0], dev) for st in steps]
     if overlap_prep:
-        main, side = torch.cuda.current_stream(dev), _side_stream(dev)
-        side.wait_stream(main)
+        # one side stream per layer: the prep kernels are small and latency bound, so they run concurrently
+        # (parallel branches of the captured graph) instead of queueing behind each other
+        main = torch.cuda.current_stream(dev)
         events = []
-        with torch.cuda.stream(side):
-            for i, st in enumerate(steps):
+        for i, st in enumerate(steps):
+            side = _side_stream(dev, i)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
                 run_step(st, None, None, None, 0, kl=kls[i], noise=noise[i], phase=L.FUSED_PREP_ONLY)
                 ev = torch.cuda.Event()
                 ev.record(side)
