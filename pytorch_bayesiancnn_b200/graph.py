@@ -21,7 +21,9 @@ class GraphedForward:
     """logits, kl = GraphedForward(net, example_x)(x).  Replay r draws Philox streams
     first_stream + r*2^20 + (0, 1, 2, ...) -- reproducible from (seed, first_stream)."""
 
-    def __init__(self, net, example_x: torch.Tensor, first_stream: int = 0, warmup: int = 2):
+    def __init__(self, net, example_x: torch.Tensor, first_stream: int = 0, warmup: int = 2, post=None):
+        """post(logits, kl) -> outputs is captured behind the forward (e.g. the multi-GPU combine with
+        its NCCL all-reduce), so a whole step is one graph launch."""
         assert example_x.is_cuda
         self.net = net
         dev = example_x.device
@@ -33,7 +35,9 @@ class GraphedForward:
         with torch.cuda.stream(side), torch.no_grad():
             for _ in range(warmup):
                 with Fn.stream_base(self.base):
-                    net(self.x)
+                    out = net(self.x)
+                if post is not None:
+                    post(*out)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
@@ -42,6 +46,8 @@ class GraphedForward:
             Fn.noise_advance(self.base, _STRIDE)
             with Fn.stream_base(self.base):
                 self.logits, self.kl = net(self.x)
+            if post is not None:
+                self.logits, self.kl = post(self.logits, self.kl)
         self.kernels_per_replay = _lib.launch_count() - n0     # engine kernels captured in the graph
         self.replays = 0
         self.reset(self.first_stream)
