@@ -294,6 +294,29 @@ def run_ours(args):
     if rank == 0:
         per_layer, roof = layer_rooflines(net, x_dev[0], args, pk, flush)
 
+    mc_batched = None
+    if rank == 0 and world == 1 and args.variant == "lrt" and args.mc_batch > 1:
+        # S Monte-Carlo samples folded into ONE launch: for LRT the samples differ only in the per-activation noise, so
+        # S samples of a batch == one batch of S*B rows (what uncertainty_estimation.py:38-41 does); KL computed once.
+        S = args.mc_batch
+        xb = x_dev[0].repeat(S, 1, 1, 1)
+        gb = bbb.GraphedForward(net, xb, first_stream=1 << 40)
+        for _ in range(3):
+            gb()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 20
+        e0.record()
+        for _ in range(reps):
+            gb()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / reps
+        mc_batched = {"mc_samples": S, "rows_per_launch": S * B, "ms_per_launch": ms,
+                      "value": S * B / (ms * 1e-3), "unit": "sample-images/s",
+                      "note": "separate figure, not the headline: S samples of the same 512 images per launch (LRT only)"}
+        del gb, xb
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference(args, seconds=args.cpu_seconds)
@@ -317,6 +340,7 @@ def run_ours(args):
             "roofline": roof,
             "per_layer": per_layer,
             "cpu_baseline": cpu,
+            "mc_batched": mc_batched,
             "wall_s_timed_loop": wall,
         }
         print(json.dumps(out), flush=True)
@@ -503,6 +527,7 @@ def main():
     ap.add_argument("--classes", type=int, default=10)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mc-batch", type=int, default=10, help="also report S MC samples folded into one launch (LRT; 0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

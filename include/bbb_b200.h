@@ -115,7 +115,8 @@ enum { BBB_LAYOUT_NCHW_F32 = 0,      /* reference layout: [B, C, H, W] fp32     
        BBB_LAYOUT_PACKED_BF16 = 1,   /* "tiled packed" bf16: the [B, F] matrix, F = H*W*C, column = (h*W + w)*C + c,
                                         C % 64 == 0, stored as [ceil(B/128)][F/64][128 rows x 128 B] with every 16 KB
                                         block in the K-major SWIZZLE_128B shared-memory image (chunk c of row r at
-                                        chunk c ^ (r & 7)); pitch arguments carry F */
+                                        chunk c ^ (r & 7)); pitch arguments carry F.  When the square is carried too
+                                        (LRT consumer) each block is [x | x^2] = 32 KB and x_sq / y_sq = base + 8192 elements */
        BBB_LAYOUT_ROWMAJOR_F32 = 2 };/* [B, OH*OW, Cout] fp32 (logits when OH*OW == 1)            */
 
 /* One Bayesian layer of a fused chain: the layer forward + KL (as bbb_conv2d_forward /

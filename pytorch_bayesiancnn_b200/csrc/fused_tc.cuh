@@ -258,6 +258,8 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
         ctl->bias[c] = p.bias_ws[n];
         ctl->bvar[c] = p.bias_ws[p.n_cblk * ng + n];
     }
+    // (A split of the K loop over two accumulator sets was tried -- the chain of dependent tcgen05.mma's is NOT
+    //  what bounds the main loop: it got 20 % slower.)
     const uint32_t tmem_cols = two ? 128u : 64u;
     if (warp == 8) tmem_alloc(smem_u32(&ctl->tmem_base), tmem_cols);
     tc_fence_before();
@@ -303,19 +305,22 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
                     const int2 item = ctl->items[i0 + u];
                     const int ipix = item.x & 0xffff, kb = item.x >> 16;
                     const uint32_t st = base + tiles_off + (uint32_t)s * stage_bytes + (uint32_t)u * unit_bytes;
-                    const size_t a_blk = (a_row0 + (size_t)ipix * p.n_kblk + kb) * (128 * 64);
-                    if (!(p.dbg_mode & 2)) {
-                        bulk_g2s(st, reinterpret_cast<const __nv_bfloat16*>(p.x) + a_blk, TC_A_BYTES, bar);
-                        if (two) bulk_g2s(st + a2_off, reinterpret_cast<const __nv_bfloat16*>(p.x_sq) + a_blk, TC_A_BYTES, bar);
-                    }
+                    // x and x^2 blocks are interleaved in global memory and adjacent in the stage: one copy
+                    const size_t a_blk = (a_row0 + (size_t)ipix * p.n_kblk + kb) * (size_t)(planes * 128 * 64);
+                    if (!(p.dbg_mode & 2))
+                        bulk_g2s(st, reinterpret_cast<const __nv_bfloat16*>(p.x) + a_blk, (uint32_t)planes * TC_A_BYTES, bar);
                     if (!(p.dbg_mode & 1)) {
                         // weight planes: [plane][group][ng rows x 128 B] -> every plane is one 64-row SW128 tile
 #pragma unroll 1
                         for (int q = 0; q < groups; ++q) {
                             const int tp = (item.y >> (8 * q)) & 0xFF;
                             const __nv_bfloat16* sp = tp != 0xFF ? p.wtiles + ((size_t)(tp * p.n_cblk + cb) * p.n_kblk + kb) * sub_elems : zero_tile;
-                            bulk_g2s(st + b_off + q * gbytes, sp, gbytes, bar);
-                            if (two) bulk_g2s(st + b_off + TC_B_BYTES + q * gbytes, tp != 0xFF ? sp + ng * 64 : zero_tile, gbytes, bar);
+                            if (groups == 1) {           // [mu | sigma^2] of the sub-tile are contiguous here and in the stage
+                                bulk_g2s(st + b_off, sp, (uint32_t)planes * gbytes, bar);
+                            } else {
+                                bulk_g2s(st + b_off + q * gbytes, sp, gbytes, bar);
+                                if (two) bulk_g2s(st + b_off + TC_B_BYTES + q * gbytes, tp != 0xFF ? sp + ng * 64 : zero_tile, gbytes, bar);
+                            }
                         }
                     }
                 }
@@ -438,7 +443,7 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
 #pragma unroll
             for (int u = 0; u < 8; ++u) r[u] = fast_act(r[u], p.act);       // act is monotone: act(max) == max(act)
             if (p.out_mode == OUT_PACKED_BF16) {          // tiled packed (N % 64 == 0 guaranteed by the host)
-                const size_t off = tiled_chunk_offset(b, pset * g.N + n0, p.out_pitch >> 6);
+                const size_t off = tiled_chunk_offset(b, pset * g.N + n0, p.out_pitch >> 6, p.y_sq ? 2 : 1);
                 *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) + off) =
                     make_uint4(pack_bf16(r[0], r[1]), pack_bf16(r[2], r[3]), pack_bf16(r[4], r[5]), pack_bf16(r[6], r[7]));
                 if (p.y_sq)
@@ -515,7 +520,10 @@ inline cudaError_t launch_fused(FusedArgs a, const void* x, const void* x_sq, cu
     a.taps = g.KHW;
     const bool lrt = a.variant == BBB_VARIANT_LRT;
     a.x = x; a.x_sq = x_sq;
-    if (do_gemm && a.planes == 2 && !x_sq) { *why = "LRT fused layer needs the squared activation"; return cudaErrorInvalidValue; }
+    if (do_gemm && a.planes == 2 && x_sq != (const void*)((const __nv_bfloat16*)x + 128 * 64)) {
+        *why = "LRT fused layer needs the activation with interleaved x / x^2 blocks (x_sq == x + 8192 elements)";
+        return cudaErrorInvalidValue;
+    }
     if (do_prep) {
         const long items = (long)a.taps * a.n_cblk * a.n_kblk * a.ng * 8;
         int grid = (int)((items + 255) / 256);

@@ -194,10 +194,12 @@ enum { OUT_PACKED_BF16 = 0, OUT_ROWMAJOR_F32 = 1, OUT_NCHW_F32 = 2 };
 // [B/128 row tiles][F/64 column blocks][128 rows x 128 B], every 16 KB block already in the K-major SWIZZLE_128B
 // smem image -- the consumer stages an A tile with ONE 16 KB cp.async.bulk instead of a 128-row tensor-map box
 // (measured: the strided box costs ~900 cycles per stage regardless of bytes, stages or CTA count).
-// Offset (in elements) of the 8-element chunk holding columns [col, col+8) of row b:
-__device__ __forceinline__ size_t tiled_chunk_offset(int b, int col, int kb_total) {
+// When a following LRT layer also needs x^2, the two planes of a block are interleaved ([block][x | x^2], 32 KB),
+// so the consumer stages both with ONE bulk copy (every cp.async.bulk costs ~200 issue cycles).
+// Offset (in elements) of the 8-element chunk holding columns [col, col+8) of row b in plane 0:
+__device__ __forceinline__ size_t tiled_chunk_offset(int b, int col, int kb_total, int planes) {
     const int r = b & 127, kb = col >> 6, ch = (col & 63) >> 3;
-    return ((size_t)(b >> 7) * kb_total + kb) * (128 * 64) + (size_t)r * 64 + (size_t)((ch ^ (r & 7)) << 3);
+    return ((size_t)(b >> 7) * kb_total + kb) * (size_t)(planes * 128 * 64) + (size_t)r * 64 + (size_t)((ch ^ (r & 7)) << 3);
 }
 
 // Epilogue math of the bf16 path: MUFU-based, a handful of instructions (the exact versions in
@@ -518,11 +520,13 @@ gemm_tc_kernel(const TcArgs p, const int stages) {
                     val = fmaxf(val, __shfl_xor_sync(0xffffffffu, val, 1));
                     val = fmaxf(val, __shfl_xor_sync(0xffffffffu, val, 2));
                 }
-                am[j] = fast_act(val, p.act);           // act is monotone: act(max) == max(act)
+                am[j] = val;
             }
             if (!writer) continue;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) am[j] = fast_act(am[j], p.act);   // writers only; act is monotone: act(max) == max(act)
             if (p.out_mode == OUT_PACKED_BF16) {          // tiled packed (N % 64 == 0 guaranteed by the host)
-                const size_t off = tiled_chunk_offset(bimg, opix * g.N + nb, p.out_pitch >> 6);
+                const size_t off = tiled_chunk_offset(bimg, opix * g.N + nb, p.out_pitch >> 6, p.y_sq ? 2 : 1);
                 *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) + off) =
                     make_uint4(pack_bf16(am[0], am[1]), pack_bf16(am[2], am[3]), pack_bf16(am[4], am[5]), pack_bf16(am[6], am[7]));
                 if (p.y_sq)

@@ -212,9 +212,10 @@ def run_step(st, nxt, cur, cur_sq, cur_pitch, kl=None, noise=None, phase=0):
         if phase == L.FUSED_PREP_ONLY:
             pitch, y, y_sq = cout * oh * ow if st.out_layout == L.LAYOUT_PACKED_BF16 else 0, None, None
         elif st.out_layout == L.LAYOUT_PACKED_BF16:
-            pitch = cout * oh * ow                   # tiled packed: [ceil(B/128)][F/64][128 x 64] bf16
-            y = torch.empty((B + 127) // 128 * 128, pitch, dtype=torch.bfloat16, device=dev)
-            y_sq = torch.empty_like(y) if (nxt is not None and nxt._variant == L.VARIANT_LRT) else None
+            pitch = cout * oh * ow                   # tiled packed: [ceil(B/128)][F/64][planes][128 x 64] bf16
+            planes = 2 if (nxt is not None and nxt._variant == L.VARIANT_LRT) else 1
+            y = torch.empty((B + 127) // 128 * 128, pitch * planes, dtype=torch.bfloat16, device=dev)
+            y_sq = y.view(-1)[128 * 64:] if planes == 2 else None      # x^2 blocks interleaved behind the x blocks
         elif st.out_layout == L.LAYOUT_ROWMAJOR_F32:
             pitch, y, y_sq = 0, torch.empty(B, cout, dtype=torch.float32, device=dev), None
         else:
