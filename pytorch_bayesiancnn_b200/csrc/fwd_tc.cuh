@@ -48,7 +48,8 @@ struct TcArgs {
     float* bias_ws;          // [2][Npad]: row 0 = bias (BBB: sampled; LRT: mu), row 1 = LRT sigma_b^2
     int n_tiles, k_blocks, planes;
     int skip_prep, prep_only;
-    int stage_x;             // stage the tile's input images in shared memory (small per-tile footprint)
+    int stage_x;             // stage the tile's input images in shared memory: 0 no, 1 as fp32, 2 as bf16 (half the
+                             // footprint: lets two LRT CTAs share an SM; x^2 is then formed from the bf16 value)
     // fused epilogue (first layer of a fused chain): 2x2 max-pool + packed bf16 output
     void* y_sq; int out_mode, out_pitch, pool;     // out_mode: 0 packed bf16 [B,(pix,c)], 2 NCHW fp32 (default)
     long long* trace;                              // debug: per-CTA clock64 checkpoints (nullptr in production)
@@ -363,6 +364,7 @@ gemm_tc_kernel(const TcArgs p, const int stages) {
     // stage layout: [A (16K)] [A^2 (16K, LRT)] [B planes (8K each)]
     const uint32_t a_off = 0, a2_off = TC_A_BYTES, b_off = (uint32_t)planes * TC_A_BYTES;
     float* xs = reinterpret_cast<float*>(sm + tiles_off + (size_t)stages * stage_bytes);   // staged input images (stage_x)
+    __nv_bfloat16* xsh = reinterpret_cast<__nv_bfloat16*>(xs);
 
     const int n_tile = blockIdx.x, m_tile = blockIdx.y;
     const int m0 = m_tile * TC_BM, n0 = n_tile * TC_BN;
@@ -390,7 +392,17 @@ gemm_tc_kernel(const TcArgs p, const int stages) {
         const int last = min(m0 + TC_BM - 1, g.M - 1) / g.OHW;
         const int nflt = (last - img0 + 1) * chw;
         const float* src = reinterpret_cast<const float*>(p.x) + (size_t)img0 * chw;
-        if (((reinterpret_cast<uintptr_t>(src) | (uintptr_t)(nflt * 4)) & 15u) == 0) {
+        const bool vec = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)(nflt * 4)) & 15u) == 0;
+        if (p.stage_x == 2) {
+            if (vec) {
+                for (int i = threadIdx.x; i < (nflt >> 2); i += blockDim.x) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+                    reinterpret_cast<uint2*>(xsh)[i] = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+                }
+            } else {
+                for (int i = threadIdx.x; i < nflt; i += blockDim.x) xsh[i] = __float2bfloat16_rn(__ldg(src + i));
+            }
+        } else if (vec) {
             for (int i = threadIdx.x; i < (nflt >> 2); i += blockDim.x)
                 reinterpret_cast<float4*>(xs)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
         } else {
@@ -455,7 +467,7 @@ gemm_tc_kernel(const TcArgs p, const int stages) {
                     const int ih = ih0 + (kt.y >> 16), iw = iw0 + (kt.y & 0xffff);
                     float val = 0.0f;
                     if (mvalid && (unsigned)ih < (unsigned)g.H && (unsigned)iw < (unsigned)g.W)
-                        val = xp[xb + kt.x];
+                        val = (p.stage_x == 2) ? __bfloat162float(xsh[xb + kt.x]) : xp[xb + kt.x];
                     v[e] = val;
                 }
                 const uint4 o = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
@@ -621,18 +633,28 @@ inline cudaError_t launch_fwd_tc(TcArgs a, cudaStream_t st, int n_sm, int* n_lau
     // short K loops (AlexNet conv1: 6 k-blocks) gain nothing from a deep ring; two stages let two CTAs share an
     // SM (2 x (2 x 48 KB) for LRT), which hides the gather latency of one CTA behind the other and halves the waves
     if (a.k_blocks <= 8 && stages > 2) stages = 2;
-    size_t smem = tc_fixed_smem(g) + (size_t)stages * tc_stage_bytes(a.planes);
-    const size_t xs_bytes = (size_t)tc_tile_images(g.OHW) * g.Cin * g.HW * 4;
-    a.stage_x = (xs_bytes <= 32 * 1024 && smem + xs_bytes <= (size_t)TC_SMEM_LIMIT) ? 1 : 0;
-    if (a.stage_x) smem += xs_bytes;
+    // exact footprint: base-alignment slack + control/k-table (rounded to 1 KB) + ring (+ staged images)
+    const size_t tiles_off = (1024 + (size_t)tc_kpad(g) * 8 + 1023) / 1024 * 1024;
+    size_t smem = 1023 + tiles_off + (size_t)stages * tc_stage_bytes(a.planes);
+    const size_t xs_elems = (size_t)tc_tile_images(g.OHW) * g.Cin * g.HW;
+    a.stage_x = 0;
+    if (xs_elems * 4 <= 32 * 1024 && smem + xs_elems * 4 <= (size_t)TC_SMEM_LIMIT) {
+        a.stage_x = 1;
+        // two CTAs per SM need 2 * (smem + 1 KB reserved) <= 228 KB: try the half-size bf16 staging when fp32 does not fit
+        const size_t per_sm = 228 * 1024;
+        if (2 * (smem + xs_elems * 4 + 1024) > per_sm && 2 * ((smem + xs_elems * 2 + 127) / 128 * 128 + 1024) <= per_sm) a.stage_x = 2;
+        smem += xs_elems * (a.stage_x == 2 ? 2 : 4);
+    }
     dim3 grid(a.n_tiles, (g.M + TC_BM - 1) / TC_BM);
     cudaError_t e;
     if (lrt) {
+        cudaFuncSetAttribute(gemm_tc_kernel<BBB_VARIANT_LRT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         e = cudaFuncSetAttribute(gemm_tc_kernel<BBB_VARIANT_LRT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         e = launch_pdl(gemm_tc_kernel<BBB_VARIANT_LRT>, grid, dim3(320), smem, st, a, stages);
         if (e != cudaSuccess) return e;
     } else {
+        cudaFuncSetAttribute(gemm_tc_kernel<BBB_VARIANT_BBB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         e = cudaFuncSetAttribute(gemm_tc_kernel<BBB_VARIANT_BBB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         e = launch_pdl(gemm_tc_kernel<BBB_VARIANT_BBB>, grid, dim3(320), smem, st, a, stages);
