@@ -234,7 +234,7 @@ int bbb_layer_forward_fused(const bbb_layer_desc* d, const void* x, const void* 
         a.prev_hw = prev_hw; a.y = y; a.y_sq = y_sq; a.out_mode = out_mode; a.out_pitch = out_pitch; a.pool = pool;
         a.in_pitch = in_pitch; a.trace = g_trace;
         const char* why = "";
-        cudaError_t e = bbb::launch_fused(a, x, x_sq, st, &nl, &why, !skip_prep, !prep_only);
+        cudaError_t e = bbb::launch_fused(a, x, x_sq, st, &nl, &why, !skip_prep, !prep_only, sm_count());
         if (e != cudaSuccess) return fail(BBB_E_CUDA, "fused tap-GEMM launch: %s %s", cudaGetErrorString(e), why);
     } else {
         return fail(BBB_E_INVALID, "bad in_layout %d", in_layout);

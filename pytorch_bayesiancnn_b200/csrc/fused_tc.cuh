@@ -41,6 +41,8 @@ struct FusedArgs {
     void* y; void* y_sq;
     int out_mode, out_pitch, pool, in_pitch;   // pitches = F (columns) of the tiled packed matrices
     long long* trace;            // debug: per-CTA clock64 checkpoints (nullptr in production)
+    int units;                   // K blocks per pipeline step (TAP_UNITS, or 1 in the two-CTAs-per-SM LRT configuration)
+    int ez_smem;                 // LRT noise: 1 = drawn into shared memory during the main loop, 0 = drawn in the epilogue
     int dbg_mma_j;               // debug: K-steps issued per stage (4 in production)
     int dbg_mode;                // debug: bit0 skip weight copies, bit1 skip A copies, bit2 free stages with a plain arrive
 };
@@ -184,8 +186,9 @@ __device__ __forceinline__ float4 act_noise4(const NoiseKey& k, int b, int pix, 
 // elected thread each; the copies of a stage are dealt round-robin so their ~100-cycle issue costs overlap).
 constexpr int TAP_THREADS = 416, TAP_NPROD = 4;
 
-template <int VARIANT>
-__global__ void __launch_bounds__(TAP_THREADS, 1)
+// MINB = resident CTAs per SM the register allocation is sized for (1: configuration A, 2: configuration B)
+template <int MINB>
+__global__ void __launch_bounds__(TAP_THREADS, MINB)
 tap_gemm_kernel(const FusedArgs p, const int stages) {
     extern __shared__ uint8_t smem_raw[];
     const Geom& g = p.g;
@@ -200,7 +203,8 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
     FusedSmem* ctl = reinterpret_cast<FusedSmem*>(sm);
     const uint32_t tiles_off = 2048u;
     const uint32_t unit_bytes = (uint32_t)planes * (TC_A_BYTES + TC_B_BYTES);   // one K block: [A][A^2][B planes]
-    const uint32_t stage_bytes = TAP_UNITS * unit_bytes;
+    const int units = p.units;
+    const uint32_t stage_bytes = (uint32_t)units * unit_bytes;
     const uint32_t a2_off = TC_A_BYTES, b_off = (uint32_t)planes * TC_A_BYTES;
     float* ez = reinterpret_cast<float*>(sm + tiles_off + (size_t)stages * stage_bytes);   // [64][128] LRT noise
 
@@ -269,7 +273,7 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
     if (tr && threadIdx.x == 0) tr[1] = clock64();
 
     const int n_items = (int)ctl->n_items;
-    const int n_steps = (n_items + TAP_UNITS - 1) / TAP_UNITS;
+    const int n_steps = (n_items + units - 1) / units;
 
     if (warp >= 9) {
         // ======================= TMA producers ==================================
@@ -297,7 +301,7 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
             mbar_wait(smem_u32(&ctl->empty[s]), ((uint32_t)(it / stages) & 1u) ^ 1u);
             if (tr && it < 40 && lane == 0) tr[48 + it] = clock64();
             if (lane == 0) {
-                const int i0 = it * TAP_UNITS, nu = min(TAP_UNITS, n_items - i0);
+                const int i0 = it * units, nu = min(units, n_items - i0);
                 const uint32_t bar = smem_u32(&ctl->full[s]);
                 mbar_arrive_expect_tx(bar, unit_tx * nu);
 #pragma unroll 1
@@ -343,7 +347,7 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
             if (tr && it == 0 && lane == 0) tr[3] = clock64();
             if (tr && it < 32 && lane == 0) tr[8 + it] = clock64();
             if (lane == 0) {
-                const int nu = min(TAP_UNITS, n_items - it * TAP_UNITS);
+                const int nu = min(units, n_items - it * units);
 #pragma unroll 1
                 for (int u = 0; u < nu; ++u) {
                     const uint32_t so = ((uint32_t)s * stage_bytes + (uint32_t)u * unit_bytes) >> 4;
@@ -369,8 +373,8 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
         const bool philox = two && !p.eps_a;
         // column c of the tile belongs to group h iff own(c): pool: channel (c & 15) >> 3 == h, else c >> 5 == h
         // (1) while the main loop runs: draw this row's LRT noise into smem (column-major, conflict free)
-        if (philox && bvalid) {
-            const NoiseKey nkey = effective_key(p.key, p.stream_base);
+        const NoiseKey nkey = effective_key(p.key, p.stream_base);
+        if (philox && bvalid && p.ez_smem) {
 #pragma unroll 1
             for (int c4 = 0; c4 < 16; ++c4) {
                 const int c = c4 * 4;
@@ -402,16 +406,25 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
 #pragma unroll 1
                 for (int q = 0; q < 4; ++q) {
                     const int c = q * 16 + i8 * 8;
-                    float am[8], av[8];
+                    float am[8], av[8], zi[8];
                     tmem_ld8(lane_base + (uint32_t)c, am);
                     if (two) tmem_ld8(lane_base + 64u + (uint32_t)c, av);
+                    if (philox && !p.ez_smem) {
+                        const int n8 = n_base + i8 * 8;
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (bvalid && n8 + 4 * hh < g.N) z = act_noise4(nkey, b, goh[q] * g.OW + gow[q], n8 + 4 * hh, g.OHW, g.N);
+                            zi[4 * hh] = z.x; zi[4 * hh + 1] = z.y; zi[4 * hh + 2] = z.z; zi[4 * hh + 3] = z.w;
+                        }
+                    }
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         float val = (any_mma ? am[u] : 0.0f) + ctl->bias[c + u];
                         if (two) {
                             const float var = 1e-16f + ((any_mma ? av[u] : 0.0f) + ctl->bvar[c + u]);
                             float e_ = 0.0f;
-                            if (philox) e_ = ez[(c + u) * 128 + t];
+                            if (philox) e_ = p.ez_smem ? ez[(c + u) * 128 + t] : zi[u];
                             else if (bvalid && n_base + i8 * 8 + u < g.N)
                                 e_ = __ldg(p.eps_a + ((size_t)b * g.N + n_base + i8 * 8 + u) * g.OHW + goh[q] * g.OW + gow[q]);
                             val = val + fast_sqrt(var) * e_;
@@ -421,16 +434,24 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
                 }
             } else {
                 const int c = i8 * 8;
-                float am[8], av[8];
+                float am[8], av[8], zi[8];
                 tmem_ld8(lane_base + (uint32_t)c, am);
                 if (two) tmem_ld8(lane_base + 64u + (uint32_t)c, av);
+                if (philox && !p.ez_smem) {
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (bvalid && n_base + c + 4 * hh < g.N) z = act_noise4(nkey, b, pset, n_base + c + 4 * hh, g.OHW, g.N);
+                        zi[4 * hh] = z.x; zi[4 * hh + 1] = z.y; zi[4 * hh + 2] = z.z; zi[4 * hh + 3] = z.w;
+                    }
+                }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     float val = (any_mma ? am[u] : 0.0f) + ctl->bias[c + u];
                     if (two) {
                         const float var = 1e-16f + ((any_mma ? av[u] : 0.0f) + ctl->bvar[c + u]);
                         float e_ = 0.0f;
-                        if (philox) e_ = ez[(c + u) * 128 + t];
+                        if (philox) e_ = p.ez_smem ? ez[(c + u) * 128 + t] : zi[u];
                         else if (bvalid && n_base + c + u < g.N)
                             e_ = __ldg(p.eps_a + ((size_t)b * g.N + n_base + c + u) * g.OHW + pset);
                         val = val + fast_sqrt(var) * e_;
@@ -510,7 +531,7 @@ inline bool fused_supported(const Geom& g, int pool) {
 }
 
 inline cudaError_t launch_fused(FusedArgs a, const void* x, const void* x_sq, cudaStream_t st, int* n_launch, const char** why,
-                                bool do_prep = true, bool do_gemm = true) {
+                                bool do_prep = true, bool do_gemm = true, int n_sm = 148) {
     const Geom& g = a.g;
     *n_launch = 0;
     a.planes = tc_planes(a.variant, a.sample);
@@ -539,21 +560,30 @@ inline cudaError_t launch_fused(FusedArgs a, const void* x, const void* x_sq, cu
     a.dbg_mma_j = 4; a.dbg_mode = 0;
     if (const char* e = getenv("BBB_B200_DBG_MODE")) a.dbg_mode = atoi(e);
     if (const char* e = getenv("BBB_B200_DBG_MMAJ")) a.dbg_mma_j = atoi(e);
-    int stages = a.planes == 2 ? 2 : 4;                              // stage = 2 K blocks: 48 KB (1 plane) / 96 KB (2 planes)
-    if (const char* e = getenv("BBB_B200_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= (a.planes == 2 ? 2 : 4)) stages = v; }   // experiment knob
-    const size_t smem = 1024 + 2048 + (size_t)stages * TAP_UNITS * tc_stage_bytes(a.planes) + (a.planes == 2 ? 64 * 128 * 4 : 0);   // align slack + control/schedule + ring + LRT noise tile
+    // Two configurations.  (A) one CTA per SM: stage = 2 K blocks, deep ring, LRT noise pre-drawn into 32 KB of smem.
+    // (B) two CTAs per SM (~99 KB each): used when the grid has more CTAs than SMs (AlexNet conv2: 192), so that all
+    // tiles run in ONE wave and one CTA's epilogue overlaps the other's main loop; LRT then draws its noise in the epilogue.
     const int psets = a.pool ? (g.OH / 2) * (g.OW / 2) : g.OHW;
+    const long n_ctas = (long)psets * a.n_cblk * ((g.B + TC_BM - 1) / TC_BM);
+    const bool two_per_sm = n_ctas > n_sm;
+    int stages;
+    if (two_per_sm) { stages = 2; a.units = a.planes == 2 ? 1 : 2; a.ez_smem = 0; }
+    else            { stages = a.planes == 2 ? 2 : 4; a.units = TAP_UNITS; a.ez_smem = 1; }
+    if (const char* e = getenv("BBB_B200_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= stages) stages = v; }   // experiment knob
+    const size_t smem = 1023 + 2048 + (size_t)stages * a.units * tc_stage_bytes(a.planes) + ((a.planes == 2 && a.ez_smem) ? 64 * 128 * 4 : 0);   // align slack + control/schedule + ring + LRT noise tile
     dim3 grid(psets * a.n_cblk, (g.B + TC_BM - 1) / TC_BM);
     cudaError_t e;
-    if (lrt) {
-        e = cudaFuncSetAttribute(tap_gemm_kernel<BBB_VARIANT_LRT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (two_per_sm) {
+        cudaFuncSetAttribute(tap_gemm_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        e = cudaFuncSetAttribute(tap_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        e = launch_pdl(tap_gemm_kernel<BBB_VARIANT_LRT>, grid, dim3(TAP_THREADS), smem, st, a, stages);
+        e = launch_pdl(tap_gemm_kernel<2>, grid, dim3(TAP_THREADS), smem, st, a, stages);
         if (e != cudaSuccess) return e;
     } else {
-        e = cudaFuncSetAttribute(tap_gemm_kernel<BBB_VARIANT_BBB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(tap_gemm_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        e = cudaFuncSetAttribute(tap_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        e = launch_pdl(tap_gemm_kernel<BBB_VARIANT_BBB>, grid, dim3(TAP_THREADS), smem, st, a, stages);
+        e = launch_pdl(tap_gemm_kernel<1>, grid, dim3(TAP_THREADS), smem, st, a, stages);
         if (e != cudaSuccess) return e;
     }
     e = cudaGetLastError();
