@@ -152,6 +152,10 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
+        # The one collective is a 61 KB all-reduce (latency bound).  Every NCCL channel is a CTA that occupies an SM
+        # while the forward kernels fill all 148 SMs at 1-2 CTAs each: keep the collective to two channels.
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", "2")
+        os.environ.setdefault("NCCL_MIN_NCHANNELS", "1")
         # NCCL prints its version banner on stdout at communicator creation: keep stdout clean for the one JSON line
         sys.stdout.flush()
         saved_fd = os.dup(1)
@@ -192,23 +196,52 @@ def run_ours(args):
     ev_reduced = [torch.cuda.Event() for _ in range(NSLOT)]
     extra_launches = [0]
 
+    # The per-step combine is captured too (one graph per slot and stream), so a step costs the host three graph
+    # launches and a few event calls instead of ~10 eager launches (which made N>1 host-bound).
+    pack_graphs, comm_graphs = [], []
+    if dist is not None:
+        from pytorch_bayesiancnn_b200 import _lib as L_
+
+        def pack(k):
+            rc = L_.lib().bbb_mc_combine(Fn._ptr(graphed.logits), 1, B, C, Fn._ptr(lo_scratch), Fn._ptr(comb[k]), Fn._stream(dev))
+            L_.check(rc, "bbb_mc_combine")
+            comb[k][3 * B * C:].copy_(graphed.kl.reshape(1))
+
+        def reduce_(k):
+            dist.all_reduce(comb[k])
+            torch.log(comb[k][:B * C] / world, out=outs[k].view(-1))
+
+        for k in range(NSLOT):                       # warm up eagerly (NCCL communicator, allocator), then capture
+            pack(k)
+            with torch.cuda.stream(comm):
+                comm.wait_stream(main)
+                reduce_(k)
+            main.wait_stream(comm)
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        for k in range(NSLOT):
+            g1 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                pack(k)
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2, stream=comm):
+                reduce_(k)
+            pack_graphs.append(g1); comm_graphs.append(g2)
+        torch.cuda.synchronize(dev)
+
     def step(i, xin=None):
         logits, kl = graphed(xin)               # forward + KL: one graph launch
         if dist is None:
             return logits, kl
-        from pytorch_bayesiancnn_b200 import _lib as L_
         k = i % NSLOT
         if i >= NSLOT:
             main.wait_event(ev_reduced[k])      # slot k is free again
-        rc = L_.lib().bbb_mc_combine(Fn._ptr(logits), 1, B, C, Fn._ptr(lo_scratch), Fn._ptr(comb[k]), Fn._stream(dev))
-        L_.check(rc, "bbb_mc_combine")
+        pack_graphs[k].replay()                 # engine MC-combine kernel + KL into comb[k]
         extra_launches[0] += 1
-        comb[k][3 * B * C:].copy_(kl.reshape(1))
         ev_packed[k].record(main)
         with torch.cuda.stream(comm):
             comm.wait_event(ev_packed[k])
-            dist.all_reduce(comb[k])
-            torch.log(comb[k][:B * C] / world, out=outs[k].view(-1))
+            comm_graphs[k].replay()             # the ONE all-reduce + log
             ev_reduced[k].record(comm)
         return outs[k], comb[k][3 * B * C]
 
