@@ -47,6 +47,7 @@ class ModuleWrapper(nn.Module):
 
     def set_flag(self, flag_name, value):
         setattr(self, flag_name, value)
+        self.__dict__.pop("_fused_plans", None)          # engine knobs (math, fuse, ...) change what can be fused
         for child in self.children():
             if hasattr(child, "set_flag"):
                 child.set_flag(flag_name, value)

@@ -134,6 +134,10 @@ def test_fused_planner_matches_reference_child_lists():
     assert fused.plan(list(n3.children()), (8, 1, 32, 32)) is None
     nl = BBBLeNet(10, 3, CFG_PRIORS); nl.set_flag("math", "bf16")
     assert fused.plan(list(nl.children()), (8, 3, 32, 32)) is None
+    # set_flag invalidates cached plans (a net first run in fp32 must still fuse after switching to bf16)
+    net.__dict__["_fused_plans"] = {(8, 3, 32, 32): None}
+    net.set_flag("math", "bf16")
+    assert "_fused_plans" not in net.__dict__
     # fp32 math is never fused
     na = BBBAlexNet(10, 3, CFG_PRIORS)
     assert fused.plan(list(na.children()), (8, 3, 32, 32)) is None
