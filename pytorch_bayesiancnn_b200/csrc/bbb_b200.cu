@@ -16,6 +16,16 @@ namespace {
 thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
 long long* g_trace = nullptr;      // debug hook (bbb_debug_set_trace)
+// debug hook (bbb_debug_set_timeline): launch k of the instrumented kernels writes [first CTA entry, last CTA
+// exit] in %globaltimer ns to g_tl[2k], g_tl[2k+1]; the slot index is fixed at launch (= capture) time
+long long* g_tl = nullptr;
+int g_tl_cap = 0, g_tl_n = 0;
+char g_tl_names[256][64];
+long long* tl_slot(bool used, const char* kind, const bbb::Geom& g) {
+    if (!g_tl || !used || g_tl_n >= g_tl_cap || g_tl_n >= 256) return nullptr;
+    snprintf(g_tl_names[g_tl_n], sizeof(g_tl_names[0]), "%s M=%d N=%d K=%d", kind, g.M, g.N, g.K);
+    return g_tl + 2 * (g_tl_n++);
+}
 
 int fail(int code, const char* fmt, ...) {
     va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
@@ -73,6 +83,7 @@ int forward_impl(const bbb_layer_desc* d, bool linear, const void* x, const floa
         a.wtiles = (__nv_bfloat16*)((char*)ws + kTcOffset);
         a.bias_ws = (float*)((char*)ws + kTcOffset + (size_t)bbb::tc_npad(g) * bbb::tc_kpad(g) * 4);
         a.skip_prep = 0; a.prep_only = 0; a.y_sq = nullptr; a.out_mode = 2; a.out_pitch = 0; a.pool = 0; a.trace = g_trace;
+        a.tl_prep = tl_slot(true, "weight_prep", g); a.tl_gemm = tl_slot(true, "gemm_tc", g);
         a.g = g; a.x = x; a.w_mu = W_mu; a.w_rho = W_rho; a.b_mu = bias_mu; a.b_rho = bias_rho;
         a.y = y; a.kl_out = kl_out; a.act_std = act_std; a.eps_a = eps_a; a.eps_b = eps_b;
         a.key = bbb::make_key(seed, stream_id); a.stream_base = (const unsigned long long*)stream_base;
@@ -216,6 +227,7 @@ int bbb_layer_forward_fused(const bbb_layer_desc* d, const void* x, const void* 
         a.wtiles = (__nv_bfloat16*)((char*)ws + kTcOffset);
         a.bias_ws = (float*)((char*)ws + kTcOffset + (size_t)bbb::tc_npad(g) * bbb::tc_kpad(g) * 4);
         a.trace = g_trace; a.skip_prep = skip_prep; a.prep_only = prep_only; a.y_sq = y_sq; a.out_mode = out_mode == 1 ? 2 : out_mode; a.out_pitch = out_pitch; a.pool = pool;
+        a.tl_prep = tl_slot(!skip_prep, "weight_prep", g); a.tl_gemm = tl_slot(!prep_only, "gemm_tc", g);
         cudaError_t e = bbb::launch_fwd_tc(a, st, sm_count(), &nl);
         if (e != cudaSuccess) return cuda_fail(e, "fused gather launch");
     } else if (in_layout == BBB_LAYOUT_PACKED_BF16) {
@@ -233,6 +245,7 @@ int bbb_layer_forward_fused(const bbb_layer_desc* d, const void* x, const void* 
         a.bias_ws = (float*)((char*)ws + kTcOffset + cpad * kpad * g.KHW * 4 + 16384);   // behind the zero sub-tile
         a.prev_hw = prev_hw; a.y = y; a.y_sq = y_sq; a.out_mode = out_mode; a.out_pitch = out_pitch; a.pool = pool;
         a.in_pitch = in_pitch; a.trace = g_trace;
+        a.tl_prep = tl_slot(!skip_prep, "tap_prep", g); a.tl_gemm = tl_slot(!prep_only, "tap_gemm", g);
         const char* why = "";
         cudaError_t e = bbb::launch_fused(a, x, x_sq, st, &nl, &why, !skip_prep, !prep_only, sm_count());
         if (e != cudaSuccess) return fail(BBB_E_CUDA, "fused tap-GEMM launch: %s %s", cudaGetErrorString(e), why);
@@ -317,6 +330,10 @@ int bbb_noise_advance(uint64_t* base, uint64_t inc, void* cuda_stream) {
 
 /* debug only (not in the public header): per-CTA clock64 checkpoints of tap_gemm_kernel */
 void bbb_debug_set_trace(void* dev_ptr) { g_trace = (long long*)dev_ptr; }
+/* debug only: timeline slots (2 x int64 per instrumented launch; caller presets [INT64_MAX, 0] before a run) */
+void bbb_debug_set_timeline(void* dev_ptr, int capacity) { g_tl = (long long*)dev_ptr; g_tl_cap = capacity; g_tl_n = 0; }
+int bbb_debug_timeline_count(void) { return g_tl_n; }
+const char* bbb_debug_timeline_name(int k) { return (k >= 0 && k < g_tl_n) ? g_tl_names[k] : ""; }
 
 const char* bbb_last_error(void) { return g_err; }
 int32_t bbb_abi_version(void) { return BBB_ABI_VERSION; }

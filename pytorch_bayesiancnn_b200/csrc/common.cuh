@@ -154,4 +154,18 @@ __device__ __forceinline__ void kl_publish(double partial, int slot, int n_slots
     }
 }
 
+
+// Debug timeline (bbb_debug_set_timeline): every instrumented launch owns two 64-bit slots,
+// [0] = earliest CTA entry, [1] = latest CTA exit, in %globaltimer nanoseconds.  nullptr in production.
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void tl_enter(long long* tl, int tid = 0) {
+    if (tl && threadIdx.x == tid) atomicMin((unsigned long long*)tl, globaltimer_ns());
+}
+__device__ __forceinline__ void tl_exit(long long* tl, int tid = 0) {
+    if (tl && threadIdx.x == tid) atomicMax((unsigned long long*)tl + 1, globaltimer_ns());
+}
 }  // namespace bbb

@@ -41,6 +41,7 @@ struct FusedArgs {
     void* y; void* y_sq;
     int out_mode, out_pitch, pool, in_pitch;   // pitches = F (columns) of the tiled packed matrices
     long long* trace;            // debug: per-CTA clock64 checkpoints (nullptr in production)
+    long long* tl_prep; long long* tl_gemm;   // debug: timeline slots of the two launches (nullptr in production)
     int units;                   // K blocks per pipeline step (TAP_UNITS, or 1 in the two-CTAs-per-SM LRT configuration)
     int ez_smem;                 // LRT noise: 1 = drawn into shared memory during the main loop, 0 = drawn in the epilogue
     int dbg_mma_j;               // debug: K-steps issued per stage (4 in production)
@@ -68,6 +69,7 @@ tap_prep_kernel(const FusedArgs p) {
     const int per_sub = p.ng * 8;                                  // (row, 8-wide K chunk) items per sub-tile
     const long n_items = (long)p.taps * p.n_cblk * p.n_kblk * per_sub;
     double kl_acc = 0.0;
+    tl_enter(p.tl_prep);
     for (long gi = (long)blockIdx.x * blockDim.x + threadIdx.x; gi < n_items; gi += (long)gridDim.x * blockDim.x) {
         const int st = (int)(gi / per_sub), item = (int)(gi - (long)st * per_sub);
         const int kb = st % p.n_kblk, cb = (st / p.n_kblk) % p.n_cblk, tap = st / (p.n_kblk * p.n_cblk);
@@ -128,6 +130,7 @@ tap_prep_kernel(const FusedArgs p) {
         const double tot = block_sum(kl_acc, red);
         if (threadIdx.x == 0) kl_publish(tot, blockIdx.x, gridDim.x, p.kl_partials, p.kl_counter, p.kl_out);
     }
+    tl_exit(p.tl_prep);
 }
 
 // ------------------------------------------------------------- TMA helpers
@@ -226,6 +229,7 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
     // [48,88) producer 0: empty[s] passed at step it, [88,128) producer 0: step it issued
     long long* tr = p.trace ? p.trace + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 128 : nullptr;
     if (tr && threadIdx.x == 0) tr[0] = clock64();
+    tl_enter(p.tl_gemm);
     pdl_trigger();
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
@@ -255,12 +259,6 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
             for (int kb = 0; kb < p.n_kblk; ++kb) ctl->items[n++] = make_int2(ipix | (kb << 16), taps);
         }
         ctl->n_items = (uint32_t)n;
-    }
-    if (threadIdx.x < 64) {                              // bias / bias variance of this tile's columns
-        const int c = threadIdx.x;
-        const int n = p.pool ? (cb * 16 + (c & 15)) : (cb * 64 + c);
-        ctl->bias[c] = p.bias_ws[n];
-        ctl->bvar[c] = p.bias_ws[p.n_cblk * ng + n];
     }
     // (A split of the K loop over two accumulator sets was tried -- the chain of dependent tcgen05.mma's is NOT
     //  what bounds the main loop: it got 20 % slower.)
@@ -390,6 +388,13 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
         const bool any_mma = n_items > 0;  // did the schedule of warp 8 contain at least one step?
         // (2) accumulator ready
         pdl_wait();                                      // our output buffers may still be read by the previous step's consumer
+        if (threadIdx.x < 64) {                          // bias / bias variance of this tile's columns (written by the prep
+            const int c = threadIdx.x;                   // kernel, which may be the programmatic predecessor: after the wait)
+            const int n = p.pool ? (cb * 16 + (c & 15)) : (cb * 64 + c);
+            ctl->bias[c] = p.bias_ws[n];
+            ctl->bvar[c] = p.bias_ws[p.n_cblk * ng + n];
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // the eight epilogue warps only
         mbar_wait(smem_u32(&ctl->accum), 0u);
         tc_fence_after();
         if (tr && threadIdx.x == 0) tr[5] = clock64();
@@ -491,6 +496,7 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
     tc_fence_after();
     if (warp == 8) tmem_dealloc(tmem, tmem_cols);
     if (tr && threadIdx.x == 256) tr[7] = clock64();
+    tl_exit(p.tl_gemm, 256);
 }
 
 // ------------------------------------------------------------- host side
@@ -550,6 +556,14 @@ inline cudaError_t launch_fused(FusedArgs a, const void* x, const void* x_sq, cu
         int grid = (int)((items + 255) / 256);
         if (grid > 2048) grid = 2048;
         if (grid < 1) grid = 1;
+        static const bool carve = [] {           // see launch_fwd_tc: keep every kernel of the chain on one smem carve-out
+            const char* e = getenv("BBB_B200_PREP_CARVEOUT");
+            if (e && e[0] == '0') return false;
+            cudaFuncSetAttribute(tap_prep_kernel<BBB_VARIANT_LRT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(tap_prep_kernel<BBB_VARIANT_BBB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            return true;
+        }();
+        (void)carve;
         if (lrt) tap_prep_kernel<BBB_VARIANT_LRT><<<grid, 256, 0, st>>>(a);
         else     tap_prep_kernel<BBB_VARIANT_BBB><<<grid, 256, 0, st>>>(a);
         cudaError_t e = cudaGetLastError();

@@ -53,6 +53,7 @@ struct TcArgs {
     // fused epilogue (first layer of a fused chain): 2x2 max-pool + packed bf16 output
     void* y_sq; int out_mode, out_pitch, pool;     // out_mode: 0 packed bf16 [B,(pix,c)], 2 NCHW fp32 (default)
     long long* trace;                              // debug: per-CTA clock64 checkpoints (nullptr in production)
+    long long* tl_prep; long long* tl_gemm;        // debug: timeline slots of the two launches (nullptr in production)
 };
 
 constexpr int TC_BM = 128, TC_BN = 64, TC_BK = 64;
@@ -154,8 +155,10 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 
 inline bool pdl_enabled() {
     static int v = -1;
-    // opt-in: measured no gain inside the captured graph (round 1)
-    if (v < 0) { const char* e = getenv("BBB_B200_PDL"); v = (e && e[0] == '1') ? 1 : 0; }
+    // on by default: inside the captured chain the next GEMM's prologue (barriers, TMEM, K schedule, first copies of
+    // its own weights) overlaps the previous GEMM's epilogue: -5 us (LRT) / -10 us (BBB) per BBBAlexNet forward
+    // (tools/timeline.py).  BBB_B200_PDL=0 turns it off.
+    if (v < 0) { const char* e = getenv("BBB_B200_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
     return v == 1;
 }
 // <<<grid, block, smem, stream>>> with the programmatic-stream-serialization attribute when enabled
@@ -276,6 +279,7 @@ weight_prep_kernel(const TcArgs p) {
     constexpr int PER_TILE = TC_BN * (TC_BK / 8);                   // (row, 8-wide K chunk) items per tile
     const long n_items = (long)p.n_tiles * p.k_blocks * PER_TILE;
     double kl_acc = 0.0;
+    tl_enter(p.tl_prep);
     for (long gi = (long)blockIdx.x * blockDim.x + threadIdx.x; gi < n_items; gi += (long)gridDim.x * blockDim.x) {
         const int tile = (int)(gi / PER_TILE), item = (int)(gi - (long)tile * PER_TILE);
         const int nt = tile / p.k_blocks, kb = tile - nt * p.k_blocks;
@@ -328,6 +332,7 @@ weight_prep_kernel(const TcArgs p) {
         const double tot = block_sum(kl_acc, red);
         if (threadIdx.x == 0) kl_publish(tot, blockIdx.x, gridDim.x, p.kl_partials, p.kl_counter, p.kl_out);
     }
+    tl_exit(p.tl_prep);
 }
 
 // ----------------------------------------------------------------- (G) GEMM
@@ -373,6 +378,7 @@ gemm_tc_kernel(const TcArgs p, const int stages) {
 
     long long* tr = p.trace ? p.trace + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 128 : nullptr;
     if (tr && threadIdx.x == 0) tr[0] = clock64();
+    tl_enter(p.tl_gemm);
     pdl_trigger();
     // ---- one-time setup ------------------------------------------------------
     for (int k = threadIdx.x; k < kpad; k += blockDim.x) {
@@ -608,6 +614,7 @@ gemm_tc_kernel(const TcArgs p, const int stages) {
     tc_fence_after();
     if (warp == 8) tmem_dealloc(tmem, tmem_cols);
     if (tr && threadIdx.x == 256) tr[7] = clock64();
+    tl_exit(p.tl_gemm, 256);
 }
 
 inline cudaError_t launch_fwd_tc(TcArgs a, cudaStream_t st, int n_sm, int* n_launch) {
@@ -621,6 +628,17 @@ inline cudaError_t launch_fwd_tc(TcArgs a, cudaStream_t st, int n_sm, int* n_lau
         const long items = (long)a.n_tiles * a.k_blocks * TC_BN * (TC_BK / 8);
         int grid = (int)((items + 255) / 256);
         if (grid > 2048) grid = 2048;
+        // Same shared-memory carve-out as the GEMM kernels: an SM only changes its L1/smem split when idle, so prep
+        // CTAs running at the default (small-smem) split kept the first GEMM's CTAs off every SM they touched until
+        // their grids drained (tools/timeline.py: first GEMM 8 us after its own prep had finished).
+        static const bool carve = [] {
+            const char* e = getenv("BBB_B200_PREP_CARVEOUT");
+            if (e && e[0] == '0') return false;
+            cudaFuncSetAttribute(weight_prep_kernel<BBB_VARIANT_LRT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(weight_prep_kernel<BBB_VARIANT_BBB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            return true;
+        }();
+        (void)carve;
         if (lrt) weight_prep_kernel<BBB_VARIANT_LRT><<<grid, 256, 0, st>>>(a);
         else     weight_prep_kernel<BBB_VARIANT_BBB><<<grid, 256, 0, st>>>(a);
         cudaError_t e = cudaGetLastError();

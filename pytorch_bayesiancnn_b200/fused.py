@@ -14,6 +14,7 @@ child-by-child path.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 from torch import nn
@@ -124,29 +125,40 @@ def _side_stream(dev, i=0):
     return st
 
 
+def _prep_chains():
+    return max(1, int(os.environ.get("BBB_B200_PREP_CHAINS", "3")))
+
+
 def run(steps, x: torch.Tensor, overlap_prep: bool = True):
     """Execute a planned chain.  Returns (network output fp32, summed KL 0-dim tensor).
 
-    The parameter-only half of every layer (softplus / eps / bf16 operand tiles / KL) is
-    launched on a side stream up front and joined by events, so that -- eagerly or inside a
-    captured graph -- it runs beside the first layers instead of on the activation critical
-    path; the GEMM halves then run back to back on the calling stream."""
+    The parameter-only half of every layer (softplus / eps / bf16 operand tiles / KL) runs on side
+    streams (parallel branches of a captured graph), joined to the GEMM chain by events, so only the
+    first layer's prep is on the activation critical path.  The preps are issued in layer order over
+    a few serial chains (default 3: layers 0,3 / 1,4 / 2,5) rather than all at once: six concurrent prep
+    grids fill the machine and the first layer's prep -- the one the GEMM chain is waiting for -- was
+    scheduled last (measured with tools/timeline.py: first GEMM at 24 us instead of ~20).  The KL sum
+    depends on the preps only and runs on the side as well."""
     dev = x.device
     kls = torch.empty(len(steps), dtype=torch.float32, device=dev)
     noise = [_draw_noise(st, x.shape[0], dev) for st in steps]
     if overlap_prep:
-        # one side stream per layer: the prep kernels are small and latency bound, so they run concurrently
-        # (parallel branches of the captured graph) instead of queueing behind each other
         main = torch.cuda.current_stream(dev)
+        chains = [_side_stream(dev, c) for c in range(min(_prep_chains(), len(steps)))]
+        for side in chains:
+            side.wait_stream(main)
         events = []
         for i, st in enumerate(steps):
-            side = _side_stream(dev, i)
-            side.wait_stream(main)
+            side = chains[i % len(chains)]
             with torch.cuda.stream(side):
                 run_step(st, None, None, None, 0, kl=kls[i], noise=noise[i], phase=L.FUSED_PREP_ONLY)
                 ev = torch.cuda.Event()
                 ev.record(side)
                 events.append(ev)
+        for side in chains[1:]:
+            chains[0].wait_stream(side)
+        with torch.cuda.stream(chains[0]):
+            kl_total = kls.sum()
     cur, cur_sq, cur_pitch = x.contiguous().float(), None, 0
     for i, st in enumerate(steps):
         nxt = steps[i + 1].layer if i + 1 < len(steps) else None
@@ -156,7 +168,11 @@ def run(steps, x: torch.Tensor, overlap_prep: bool = True):
                                               phase=L.FUSED_SKIP_PREP)
         else:
             cur, cur_sq, cur_pitch = run_step(st, nxt, cur, cur_sq, cur_pitch, kl=kls[i], noise=noise[i])
-    return cur, kls.sum()
+    if overlap_prep:
+        main.wait_stream(chains[0])        # joins every side stream (chain 0 waited for the others)
+    else:
+        kl_total = kls.sum()
+    return cur, kl_total
 
 
 def _draw_noise(st, B, dev):
