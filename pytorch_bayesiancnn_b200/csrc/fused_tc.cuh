@@ -133,6 +133,119 @@ tap_prep_kernel(const FusedArgs p) {
     tl_exit(p.tl_prep);
 }
 
+// ------------------------------------------------- (P2) tap prep, conv layers
+// Same outputs as tap_prep_kernel for layers with a real kernel window (KHW > 1, prev_hw == 1), but reading the
+// parameters the way they lie in memory.  tap_prep_kernel's work item is one 16-byte output chunk = 8 input
+// channels of ONE tap, i.e. eight 4-byte loads KHW floats apart per thread and a different row per lane: every
+// warp load touches 32 lines and every 32-byte sector is fetched KHW times (by KHW different CTAs).  That made the
+// preps LSU-bound (17-32 us per AlexNet layer for 0.3-0.9 M weights) and they share the machine with the first
+// GEMMs.  Here a CTA owns R output channels x one 64-input-channel block: each row's 64*KHW floats are contiguous
+// in OIHW order and are read with consecutive lanes on consecutive floats; softplus / eps / KL are element-wise, so
+// they are applied right there; the bf16 results go through shared memory ([plane][tap][row][cin]) and leave as the
+// same pre-swizzled 16-byte chunks, 1 KB contiguous per (tap, plane).
+constexpr int PREP2_BATCH = 4;                                     // loads in flight per thread
+__host__ __device__ inline int prep2_slab(int R) { return R * 64 + 8; }   // bf16 per (plane, tap) slab; +8 keeps 16 B alignment, skews banks
+
+template <int VARIANT>
+__global__ void __launch_bounds__(256)
+tap_prep_conv_kernel(const FusedArgs p, const int R) {
+    extern __shared__ __align__(16) uint8_t prep2_smem[];
+    __shared__ double red[32];
+    constexpr bool LRT = VARIANT == BBB_VARIANT_LRT;
+    __nv_bfloat16* sm = reinterpret_cast<__nv_bfloat16*>(prep2_smem);
+    const Geom& g = p.g;
+    const NoiseKey nkey = effective_key(p.key, p.stream_base);
+    const bool stoch = p.sample != 0, do_kl = p.kl_out != nullptr;
+    const int KHW = g.KHW, L = 64 * KHW, PS = prep2_slab(R);
+    const size_t sub = fused_wtile_elems(p);
+    const int n_units = (p.n_cblk * p.ng / R) * p.n_kblk;
+    const int dc = 256 / KHW, dq = 256 - dc * KHW;                  // (cin, tap) advance of a 256-element stride
+    double kl_acc = 0.0;
+    tl_enter(p.tl_prep);
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const int rb = unit / p.n_kblk, kb = unit - rb * p.n_kblk;
+        const int n0 = rb * R, cin0 = kb * 64;
+        const int total = R * L;
+        // ---- phase 1: coalesced loads, element-wise math, bf16 into smem ----
+        int cin = threadIdx.x / KHW, tap = threadIdx.x - cin * KHW, r = 0;
+        while (cin >= 64) { cin -= 64; ++r; }
+        for (int e0 = threadIdx.x; e0 < total; e0 += 256 * PREP2_BATCH) {
+            float mu[PREP2_BATCH], rho[PREP2_BATCH];
+            size_t wi[PREP2_BATCH];
+            int so[PREP2_BATCH];                                    // smem offset of the element, -1: past the end
+            bool ok[PREP2_BATCH];
+#pragma unroll
+            for (int u = 0; u < PREP2_BATCH; ++u) {
+                const bool in = e0 + 256 * u < total;
+                const int n = n0 + r;
+                ok[u] = in && n < g.N && cin0 + cin < g.Cin;
+                wi[u] = (size_t)n * g.K + (size_t)(cin0 + cin) * KHW + tap;
+                so[u] = in ? tap * PS + r * 64 + cin : -1;
+                mu[u] = ok[u] ? __ldg(p.w_mu + wi[u]) : 0.0f;
+                rho[u] = (ok[u] && (stoch || do_kl)) ? __ldg(p.w_rho + wi[u]) : 0.0f;
+                tap += dq; cin += dc;
+                if (tap >= KHW) { tap -= KHW; ++cin; }
+                while (cin >= 64) { cin -= 64; ++r; }
+            }
+#pragma unroll
+            for (int u = 0; u < PREP2_BATCH; ++u) {
+                if (so[u] < 0) continue;
+                float wv = 0.0f, sv = 0.0f;
+                if (ok[u]) {
+                    const float sigma = (stoch || do_kl) ? softplus_sigma(rho[u]) : 0.0f;
+                    if (LRT) { wv = mu[u]; sv = sigma * sigma; }
+                    else if (stoch) {
+                        const float e_ = p.eps_a ? __ldg(p.eps_a + wi[u]) : normal1(wi[u], nkey);
+                        wv = mu[u] + e_ * sigma;
+                    } else wv = mu[u];
+                    if (do_kl) kl_acc += (double)kl_term(mu[u], sigma, p.prior_mu, p.prior_sigma, p.kl_convention);
+                }
+                sm[so[u]] = __float2bfloat16_rn(wv);
+                if (p.planes == 2) sm[KHW * PS + so[u]] = __float2bfloat16_rn(sv);
+            }
+        }
+        __syncthreads();
+        // ---- phase 2: 16-byte chunks (8 input channels of one tap) out, in the SW128 image order ----
+        const int items = p.planes * KHW * R * 8;
+        for (int it = threadIdx.x; it < items; it += 256) {
+            const int chunk = it & 7, rr = (it >> 3) % R, pt = it / (8 * R);      // pt = plane*KHW + tap
+            const int plane = pt / KHW, tp = pt - plane * KHW;
+            const uint4 v = *reinterpret_cast<const uint4*>(sm + (size_t)pt * PS + rr * 64 + chunk * 8);
+            const int n = n0 + rr, cb = n / p.ng, row = n - cb * p.ng;
+            const size_t st = ((size_t)tp * p.n_cblk + cb) * p.n_kblk + kb;
+            __nv_bfloat16* dst = p.wtiles + st * sub + (size_t)plane * p.ng * 64 + row * 64 + ((chunk ^ (row & 7)) << 3);
+            *reinterpret_cast<uint4*>(dst) = v;
+        }
+        __syncthreads();
+    }
+    // one all-zero sub-tile behind the real ones: staged for pool-window pixels whose tap is outside the kernel
+    for (long gi = (long)blockIdx.x * blockDim.x + threadIdx.x; gi < (long)(sub / 8); gi += (long)gridDim.x * blockDim.x)
+        reinterpret_cast<uint4*>(p.wtiles + (size_t)p.taps * p.n_cblk * p.n_kblk * sub)[gi] = make_uint4(0u, 0u, 0u, 0u);
+    {   // bias: prepared (and its KL counted) by the first CTAs, one thread per channel
+        const int npad = p.n_cblk * p.ng;
+        for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < npad; n += gridDim.x * blockDim.x) {
+            float bm = 0.0f, bv = 0.0f;
+            if (p.has_bias && n < g.N) {
+                const float mu = __ldg(p.b_mu + n);
+                const float sigma = (stoch || do_kl) ? softplus_sigma(__ldg(p.b_rho + n)) : 0.0f;
+                if (LRT) { bm = mu; bv = sigma * sigma; }
+                else if (stoch) {
+                    const float e_ = p.eps_b ? __ldg(p.eps_b + n) : normal1((uint64_t)g.N * g.K + n, nkey);
+                    bm = mu + e_ * sigma;
+                } else bm = mu;
+                if (do_kl) kl_acc += (double)kl_term(mu, sigma, p.prior_mu, p.prior_sigma, p.kl_convention);
+            }
+            p.bias_ws[n] = bm;
+            p.bias_ws[npad + n] = bv;
+        }
+    }
+    if (do_kl) {
+        const double tot = block_sum(kl_acc, red);
+        if (threadIdx.x == 0) kl_publish(tot, blockIdx.x, gridDim.x, p.kl_partials, p.kl_counter, p.kl_out);
+    }
+    tl_exit(p.tl_prep);
+}
+
 // ------------------------------------------------------------- TMA helpers
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
     asm volatile(
@@ -564,8 +677,30 @@ inline cudaError_t launch_fused(FusedArgs a, const void* x, const void* x_sq, cu
             return true;
         }();
         (void)carve;
-        if (lrt) tap_prep_kernel<BBB_VARIANT_LRT><<<grid, 256, 0, st>>>(a);
-        else     tap_prep_kernel<BBB_VARIANT_BBB><<<grid, 256, 0, st>>>(a);
+        // conv layers: the coalesced variant (rows x 64-channel block per CTA); R = rows per CTA, shrunk until the
+        // grid covers the SMs and the staging tile fits 48 KB
+        static const bool prep2_on = [] { const char* e = getenv("BBB_B200_PREP2"); return !(e && e[0] == '0'); }();
+        int R = 8;
+        const int npad = a.n_cblk * a.ng;
+        auto need = [&](int r) { return (size_t)a.planes * g.KHW * prep2_slab(r) * 2; };
+        while (R > 2 && ((long)(npad / R) * a.n_kblk < n_sm || need(R) > 48 * 1024)) R >>= 1;
+        const bool prep2 = prep2_on && g.KHW > 1 && a.prev_hw == 1 && g.Cin % 64 == 0 && a.taps == g.KHW && need(R) <= 48 * 1024;
+        if (prep2) {
+            static const bool carve2 = [] {
+                const char* e = getenv("BBB_B200_PREP_CARVEOUT");
+                if (e && e[0] == '0') return false;
+                cudaFuncSetAttribute(tap_prep_conv_kernel<BBB_VARIANT_LRT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                cudaFuncSetAttribute(tap_prep_conv_kernel<BBB_VARIANT_BBB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                return true;
+            }();
+            (void)carve2;
+            int grid2 = (npad / R) * a.n_kblk;
+            if (grid2 > 2048) grid2 = 2048;
+            if (lrt) tap_prep_conv_kernel<BBB_VARIANT_LRT><<<grid2, 256, need(R), st>>>(a, R);
+            else     tap_prep_conv_kernel<BBB_VARIANT_BBB><<<grid2, 256, need(R), st>>>(a, R);
+        }
+        else if (lrt) tap_prep_kernel<BBB_VARIANT_LRT><<<grid, 256, 0, st>>>(a);
+        else          tap_prep_kernel<BBB_VARIANT_BBB><<<grid, 256, 0, st>>>(a);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         *n_launch += 1;

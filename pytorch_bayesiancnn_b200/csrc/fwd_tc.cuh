@@ -155,9 +155,9 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 
 inline bool pdl_enabled() {
     static int v = -1;
-    // on by default: inside the captured chain the next GEMM's prologue (barriers, TMEM, K schedule, first copies of
-    // its own weights) overlaps the previous GEMM's epilogue: -5 us (LRT) / -10 us (BBB) per BBBAlexNet forward
-    // (tools/timeline.py).  BBB_B200_PDL=0 turns it off.
+    // on by default: inside the captured chain the next GEMM's CTAs start on idle SMs while the previous GEMM is
+    // still in its epilogue, so its prologue (barriers, TMEM, K schedule, LRT noise tile) is done by the time its
+    // inputs are: -5 us (LRT) / -10 us (BBB) per BBBAlexNet forward (tools/timeline.py).  BBB_B200_PDL=0 turns it off.
     if (v < 0) { const char* e = getenv("BBB_B200_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
     return v == 1;
 }
