@@ -21,7 +21,6 @@
 //        warps 0-3 : epilogue -- tcgen05.ld, bias, LRT sqrt(var)*eps, 2x2 max-pool across
 //                 the four column groups, activation, packed bf16 (+square) or fp32 store
 #pragma once
-#include <cuda.h>
 #include "fwd_tc.cuh"
 
 namespace bbb {
@@ -246,12 +245,7 @@ tap_prep_conv_kernel(const FusedArgs p, const int R) {
     tl_exit(p.tl_prep);
 }
 
-// ------------------------------------------------------------- TMA helpers
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-        ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(bar) : "memory");
-}
+// ------------------------------------------------------------- UMMA helpers
 // K-major SWIZZLE_128B descriptor: 8-row groups 1024 B apart, layout_type = 2 at [61,64)
 __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
@@ -613,33 +607,6 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
 }
 
 // ------------------------------------------------------------- host side
-typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-inline PFN_tmapEncodeTiled tmap_encoder() {
-    static PFN_tmapEncodeTiled fn = nullptr;
-    if (!fn) {
-        void* f = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = (PFN_tmapEncodeTiled)f;
-    }
-    return fn;
-}
-// packed bf16 activation [rows, cols] with row pitch `pitch` elements -> box [64 cols x 128 rows], 128B swizzle
-inline bool make_act_tmap(CUtensorMap* tm, const void* ptr, int rows, int cols, int pitch) {
-    PFN_tmapEncodeTiled enc = tmap_encoder();
-    if (!enc) return false;
-    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t gstr[1] = {(cuuint64_t)pitch * 2};
-    cuuint32_t box[2] = {64, 128};
-    cuuint32_t estr[2] = {1, 1};
-    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 inline bool fused_supported(const Geom& g, int pool) {
     if (g.DH != 1 || g.DW != 1) return false;
     if (g.HW > 64) return false;                       // "small map" regime
