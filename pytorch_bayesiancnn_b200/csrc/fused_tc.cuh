@@ -1,13 +1,14 @@
 // Fused tcgen05 pipeline for chains of Bayesian layers on small feature maps.
 //
-// Between fused layers the activation lives in HBM as a "packed" bf16 matrix
-// [batch, (pixel, channel)] (NHWC flattened, row pitch padded to 8 elements) plus,
-// for the LRT variant, its element-wise square -- so the next layer's A operand is
-// a plain 2-D TMA box and x^2 never has to be recomputed.
+// Between fused layers the activation lives in HBM "tiled packed": [B/128][F/64][planes] blocks of
+// 128 rows x 128 B (64 bf16 of the NHWC-flattened (pixel, channel) axis), each block already in the
+// SWIZZLE_128B shared-memory image, written that way by the producing epilogue; for LRT consumers the
+// element-wise square is interleaved behind every x block -- so an A (A^2) tile is ONE 16 KB cp.async.bulk
+// and x^2 never has to be recomputed.
 //
-//  (P) tap_prep_kernel : like weight_prep_kernel but emits the weights tap-major:
-//      [tap][cout block][cin block][plane][NG x 64] bf16 sub-tiles in canonical
-//      K-major core-matrix order.  softplus / eps / KL exactly once per weight.
+//  (P) tap_prep_kernel / tap_prep_conv_kernel : like weight_prep_kernel but tap-major:
+//      [tap][cout block][cin block][plane][NG x 64] bf16 sub-tiles, pre-swizzled, + one zero sub-tile.
+//      softplus / eps / KL exactly once per weight.
 //
 //  (G) tap_gemm_kernel : "conv on a small map == block-structured dense layer".
 //      Rows = 128 images, K walks (input pixel, 64-channel block), each output
@@ -15,11 +16,12 @@
 //      tap that links the group's output pixel to the input pixel is computed; if
 //      it falls outside the kernel window the MMA (and the weight copy) is skipped
 //      -- zero padding costs nothing (AlexNet conv3-5: 4 of 9 taps are live).
-//        warp 5 : TMA producer -- cp.async.bulk.tensor.2d for A (and A^2), 128B swizzle;
-//                 cp.async.bulk for the live weight sub-tiles
-//        warp 4 : tcgen05.mma issuer (M=128, N=NG, bf16 -> fp32 TMEM; LRT: 2nd plane)
-//        warps 0-3 : epilogue -- tcgen05.ld, bias, LRT sqrt(var)*eps, 2x2 max-pool across
-//                 the four column groups, activation, packed bf16 (+square) or fp32 store
+//        warps 9-12 : producers (each owns ring stages): cp.async.bulk of A / A^2 blocks and of the
+//                     live weight sub-tiles, mbarrier complete_tx
+//        warp 8     : tcgen05.mma issuer (M=128, N=64, bf16 -> fp32 TMEM; LRT: 2nd accumulator)
+//        warps 0-7  : LRT noise tile (Philox) during the main loop, then the epilogue -- tcgen05.ld,
+//                     bias, sqrt(var)*eps, 2x2 max-pool across the four column groups, activation,
+//                     tiled-packed bf16 (+square) or fp32 store
 #pragma once
 #include "fwd_tc.cuh"
 
