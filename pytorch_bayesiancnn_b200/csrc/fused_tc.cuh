@@ -687,7 +687,10 @@ inline cudaError_t launch_fused(FusedArgs a, const void* x, const void* x_sq, cu
     int stages;
     if (two_per_sm) { stages = 2; a.units = a.planes == 2 ? 1 : 2; a.ez_smem = 0; }
     else            { stages = a.planes == 2 ? 2 : 4; a.units = TAP_UNITS; a.ez_smem = 1; }
-    if (const char* e = getenv("BBB_B200_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= stages) stages = v; }   // experiment knob
+    // experiment knobs: BBB_B200_UNITS=1 -> configuration A with one K block per stage and four stages (same
+    // shared-memory footprint for LRT, finer-grained hand-offs); BBB_B200_STAGES lowers the ring depth
+    if (const char* e = getenv("BBB_B200_UNITS")) { if (atoi(e) == 1 && !two_per_sm) { a.units = 1; stages = 4; } }
+    if (const char* e = getenv("BBB_B200_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= stages) stages = v; }
     const size_t smem = 1023 + 2048 + (size_t)stages * a.units * tc_stage_bytes(a.planes) + ((a.planes == 2 && a.ez_smem) ? 64 * 128 * 4 : 0);   // align slack + control/schedule + ring + LRT noise tile
     dim3 grid(psets * a.n_cblk, (g.B + TC_BM - 1) / TC_BM);
     cudaError_t e;
