@@ -192,7 +192,9 @@ def run_ours(args):
     # (softmax / softmax^2 / logit sums), then ONE NCCL all-reduce of [3*B*C + 1] floats per step.  The collective
     # runs on its own stream, double buffered, so step i's all-reduce overlaps step i+1's forward.
     NSLOT = 2
-    comm = torch.cuda.Stream(device=dev) if dist is not None else None
+    # High priority: the all-reduce's two CTAs must not queue behind the forward's kernels, which (chained by PDL)
+    # hand every freed SM straight to the next GEMM; a late collective stalls the two-slot ring below.
+    comm = torch.cuda.Stream(device=dev, priority=-1) if dist is not None else None
     comb = [torch.zeros(3 * B * C + 1, dtype=torch.float32, device=dev) for _ in range(NSLOT)]
     outs = [torch.empty(B, C, dtype=torch.float32, device=dev) for _ in range(NSLOT)]
     lo_scratch = torch.empty(B, C, dtype=torch.float32, device=dev)
