@@ -378,10 +378,11 @@ def run_ours(args):
             "data": "synthetic (randn inputs, random-init params N(0,0.1)/rho N(-5,0.1))",
             "config": {"workload": f"BBBAlexNet-{C} CIFAR-10 shape 3x32x32, batch {B}, {args.variant} layers, "
                                    f"softplus, 1 MC sample per GPU per step (MC samples sharded over GPUs)",
-                       "named_config": "BASELINE.json configs[2] (BBBAlexNet CIFAR-10 batch 512 bf16, 10 MC samples, 1xB200, "
-                                       "BBB_LRT): a step is ONE MC sample of the batch and the metric counts image-samples "
-                                       "(B*S/t, SURVEY 8d), so the 10-sample loop has this same throughput; the single-launch "
-                                       "S=10 figure is reported separately under mc_batched",
+                       "named_config": ("BASELINE.json configs[2] (BBBAlexNet CIFAR-10 batch 512 bf16, 10 MC samples, 1xB200, "
+                                        "BBB_LRT): a step is ONE MC sample of the batch and the metric counts image-samples "
+                                        "(B*S/t, SURVEY 8d), so the 10-sample loop has this same throughput; the single-launch "
+                                        "S=10 figure is reported separately under mc_batched")
+                       if (args.variant, args.math, B, C) == ("lrt", "bf16", 512, 10) else None,
                        "batch": B, "variant": args.variant, "math": args.math, "mc_samples_total": world,
                        "parallelism": f"mc{world}", "l2": "no flush: inputs rotate through 24 resident batches = 151 MB > 126 MB L2",
                        "launch": "CUDA graph replay of the full forward (noise advance, per-layer prep + GEMM kernels, KL sum); one captured graph per resident input batch, read in place"},
