@@ -248,6 +248,12 @@ tap_prep_conv_kernel(const FusedArgs p, const int R) {
 }
 
 // ------------------------------------------------------------- UMMA helpers
+// two packed bf16 -> their squares (exact product, one rounding: same value as bf16(float(x) * float(x)))
+__device__ __forceinline__ uint32_t bf16x2_sq(uint32_t v) {
+    __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&v);
+    h = __hmul2(h, h);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
 // K-major SWIZZLE_128B descriptor: 8-row groups 1024 B apart, layout_type = 2 at [61,64)
 __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
@@ -266,6 +272,7 @@ struct FusedSmem {
     // hand-off (~500-900 cycles measured: barrier round trip + TMA issue + first-MMA start-up) is paid per STEP.
     int2 items[TAP_MAX_ITEMS];
     int taps_px[64];                // per input pixel: packed taps (staging for the schedule build)
+    unsigned long long sq[4];       // SQ variant only: "A^2 of stage s is ready" (kept last: the other offsets do not move)
 };
 
 // tap linking output pixel (oh,ow) with input pixel (ih,iw); -1 if outside the kernel window
@@ -298,8 +305,12 @@ __device__ __forceinline__ float4 act_noise4(const NoiseKey& k, int b, int pix, 
 // elected thread each; the copies of a stage are dealt round-robin so their ~100-cycle issue costs overlap).
 constexpr int TAP_THREADS = 416, TAP_NPROD = 4;
 
+// SQ (experimental, BBB_B200_SQ_ONCHIP=1, LRT only): the activation arrives WITHOUT its x^2 blocks; the producer warp
+// that owns a stage squares the landed A tile into the stage's A^2 slot (element-wise, layout-agnostic: both tiles
+// share the SW128 image) and signals sq[s]; the MMA warp issues the mean MMAs first and the variance MMAs after sq[s].
+// Cuts the bytes a K block pulls through L2 from 48 KB to 32 KB and halves the activation traffic between layers.
 // MINB = resident CTAs per SM the register allocation is sized for (1: configuration A, 2: configuration B)
-template <int MINB>
+template <int MINB, bool SQ = false>
 __global__ void __launch_bounds__(TAP_THREADS, MINB)
 tap_gemm_kernel(const FusedArgs p, const int stages) {
     extern __shared__ uint8_t smem_raw[];
@@ -346,6 +357,7 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
             mbar_init(smem_u32(&ctl->empty[s]), 1);
         }
         mbar_init(smem_u32(&ctl->accum), 1);
+        if constexpr (SQ) for (int s = 0; s < stages; ++s) mbar_init(smem_u32(&ctl->sq[s]), 1);
         fence_barrier_init();
     }
     // K-loop schedule: one thread per input pixel works out the taps (integer divisions), thread 64 compacts
@@ -398,7 +410,8 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
         const size_t sub_elems = (size_t)planes * ng * 64;
         const __nv_bfloat16* zero_tile = p.wtiles + (size_t)p.taps * p.n_cblk * p.n_kblk * sub_elems;
         const uint32_t gbytes = (uint32_t)ng * 128;                     // one group, one plane
-        const uint32_t unit_tx = ((p.dbg_mode & 2) ? 0u : (uint32_t)planes * TC_A_BYTES) +
+        const uint32_t a_copy = SQ ? (uint32_t)TC_A_BYTES : (uint32_t)planes * TC_A_BYTES;   // SQ: x only, x^2 formed here
+        const uint32_t unit_tx = ((p.dbg_mode & 2) ? 0u : a_copy) +
                                  ((p.dbg_mode & 1) ? 0u : (uint32_t)(groups * planes) * gbytes);
         const size_t a_row0 = (size_t)blockIdx.y * (p.in_pitch >> 6);   // first 16 KB block of this row tile
 #pragma unroll 1
@@ -417,9 +430,9 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
                     const int ipix = item.x & 0xffff, kb = item.x >> 16;
                     const uint32_t st = base + tiles_off + (uint32_t)s * stage_bytes + (uint32_t)u * unit_bytes;
                     // x and x^2 blocks are interleaved in global memory and adjacent in the stage: one copy
-                    const size_t a_blk = (a_row0 + (size_t)ipix * p.n_kblk + kb) * (size_t)(planes * 128 * 64);
+                    const size_t a_blk = (a_row0 + (size_t)ipix * p.n_kblk + kb) * (size_t)((SQ ? 1 : planes) * 128 * 64);
                     if (!(p.dbg_mode & 2))
-                        bulk_g2s(st, reinterpret_cast<const __nv_bfloat16*>(p.x) + a_blk, (uint32_t)planes * TC_A_BYTES, bar);
+                        bulk_g2s(st, reinterpret_cast<const __nv_bfloat16*>(p.x) + a_blk, a_copy, bar);
                     if (!(p.dbg_mode & 1)) {
                         // weight planes: [plane][group][ng rows x 128 B] -> every plane is one 64-row SW128 tile
 #pragma unroll 1
@@ -438,6 +451,25 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
                 if (tr && it < 40) tr[88 + it] = clock64();
             }
             __syncwarp();                                // stay converged: the next blocking wait must be a whole-warp wait
+            if constexpr (SQ) {
+                // this warp owns stage s: wait for its data, square A into the A^2 slot, tell the MMA warp
+                mbar_wait(smem_u32(&ctl->full[s]), (uint32_t)(it / stages) & 1u);
+                const int nu = min(units, n_items - it * units);
+                for (int u = 0; u < nu; ++u) {
+                    uint8_t* a_tile = sm + tiles_off + (size_t)s * stage_bytes + (size_t)u * unit_bytes;
+#pragma unroll 4
+                    for (int c = lane; c < TC_A_BYTES / 16; c += 32) {
+                        const uint4 v = *reinterpret_cast<const uint4*>(a_tile + c * 16);
+                        uint4 q;
+                        q.x = bf16x2_sq(v.x); q.y = bf16x2_sq(v.y); q.z = bf16x2_sq(v.z); q.w = bf16x2_sq(v.w);
+                        *reinterpret_cast<uint4*>(a_tile + a2_off + c * 16) = q;
+                    }
+                }
+                fence_proxy_async();                     // generic-proxy stores -> visible to the tensor core
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&ctl->sq[s]));
+                __syncwarp();
+            }
         }
     } else if (warp == 8) {
         // ======================= MMA issuer =====================================
@@ -463,10 +495,29 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
                     for (int j = 0; j < 4; ++j) {
                         if (j >= p.dbg_mma_j) break;
                         umma_bf16(tmem, da + 2 * j, db + 2 * j, idesc, (it | u | j) ? 1u : 0u);
-                        if (two) umma_bf16(tmem + 64u, da + (a2_off >> 4) + 2 * j, db + (TC_B_BYTES >> 4) + 2 * j, idesc, (it | u | j) ? 1u : 0u);
+                        if (!SQ && two) umma_bf16(tmem + 64u, da + (a2_off >> 4) + 2 * j, db + (TC_B_BYTES >> 4) + 2 * j, idesc, (it | u | j) ? 1u : 0u);
                     }
                 }
-                if (p.dbg_mode & 4) mbar_arrive(smem_u32(&ctl->empty[s])); else umma_commit(smem_u32(&ctl->empty[s]));
+                if constexpr (!SQ) {
+                    if (p.dbg_mode & 4) mbar_arrive(smem_u32(&ctl->empty[s])); else umma_commit(smem_u32(&ctl->empty[s]));
+                }
+            }
+            if constexpr (SQ) {                          // variance MMAs once the squared tiles of this stage are in place
+                __syncwarp();
+                mbar_wait(smem_u32(&ctl->sq[s]), (uint32_t)(it / stages) & 1u);      // whole-warp wait
+                tc_fence_after();
+                if (lane == 0) {
+                    const int nu = min(units, n_items - it * units);
+#pragma unroll 1
+                    for (int u = 0; u < nu; ++u) {
+                        const uint32_t so = ((uint32_t)s * stage_bytes + (uint32_t)u * unit_bytes) >> 4;
+                        const uint64_t da = dA0 + so, db = dB0 + so;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            umma_bf16(tmem + 64u, da + (a2_off >> 4) + 2 * j, db + (TC_B_BYTES >> 4) + 2 * j, idesc, (it | u | j) ? 1u : 0u);
+                    }
+                    umma_commit(smem_u32(&ctl->empty[s]));
+                }
             }
             __syncwarp();
         }
@@ -629,7 +680,14 @@ inline cudaError_t launch_fused(FusedArgs a, const void* x, const void* x_sq, cu
     a.taps = g.KHW;
     const bool lrt = a.variant == BBB_VARIANT_LRT;
     a.x = x; a.x_sq = x_sq;
-    if (do_gemm && a.planes == 2 && x_sq != (const void*)((const __nv_bfloat16*)x + 128 * 64)) {
+    // experimental (not yet validated on hardware): LRT input arrives without x^2 blocks, squares formed on chip
+    static const bool sq_env = [] { const char* e = getenv("BBB_B200_SQ_ONCHIP"); return e && e[0] == '1'; }();
+    const bool sq = sq_env && a.planes == 2;
+    if (do_gemm && sq && x_sq != nullptr) {
+        *why = "BBB_B200_SQ_ONCHIP: the LRT activation must come without x^2 blocks (x_sq == NULL)";
+        return cudaErrorInvalidValue;
+    }
+    if (do_gemm && !sq && a.planes == 2 && x_sq != (const void*)((const __nv_bfloat16*)x + 128 * 64)) {
         *why = "LRT fused layer needs the activation with interleaved x / x^2 blocks (x_sq == x + 8192 elements)";
         return cudaErrorInvalidValue;
     }
@@ -694,7 +752,16 @@ inline cudaError_t launch_fused(FusedArgs a, const void* x, const void* x_sq, cu
     const size_t smem = 1023 + 2048 + (size_t)stages * a.units * tc_stage_bytes(a.planes) + ((a.planes == 2 && a.ez_smem) ? 64 * 128 * 4 : 0);   // align slack + control/schedule + ring + LRT noise tile
     dim3 grid(psets * a.n_cblk, (g.B + TC_BM - 1) / TC_BM);
     cudaError_t e;
-    if (two_per_sm) {
+    if (sq) {
+        auto launch = [&](auto kernel) {
+            cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaError_t e2 = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e2 != cudaSuccess) return e2;
+            return launch_pdl(kernel, grid, dim3(TAP_THREADS), smem, st, a, stages);
+        };
+        e = two_per_sm ? launch(tap_gemm_kernel<2, true>) : launch(tap_gemm_kernel<1, true>);
+        if (e != cudaSuccess) return e;
+    } else if (two_per_sm) {
         cudaFuncSetAttribute(tap_gemm_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         e = cudaFuncSetAttribute(tap_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
