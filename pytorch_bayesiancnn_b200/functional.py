@@ -119,6 +119,20 @@ def _require_cuda(t: torch.Tensor, what: str):
 
 
 _ws_cache: dict = {}
+_ws_slot = 0
+
+
+@contextlib.contextmanager
+def workspace_slot(k: int):
+    """Layer workspaces (prepared operand tiles, KL partials and counters) are private per (layer, slot).
+    Forwards that may run CONCURRENTLY -- e.g. two captured graphs replayed on two streams -- must be built
+    under different slots; everything on one stream can share slot 0 (the default)."""
+    global _ws_slot
+    prev, _ws_slot = _ws_slot, int(k)
+    try:
+        yield
+    finally:
+        _ws_slot = prev
 
 
 def workspace(device, desc=None, owner=None) -> torch.Tensor:
@@ -128,7 +142,8 @@ def workspace(device, desc=None, owner=None) -> torch.Tensor:
     which on the tcgen05 path also holds that layer's prepared bf16 operand tiles."""
     n = int(L.lib().bbb_workspace_bytes(C.byref(desc) if desc is not None else None))
     # a layer-private buffer is keyed by the layer only: zero-filled once, never re-created per stream/graph
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream if owner is None else None, owner)
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream if owner is None else None, owner,
+           _ws_slot if owner is not None else 0)
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < n:
         ws = torch.zeros(n, dtype=torch.uint8, device=device)

@@ -26,9 +26,11 @@ class GraphedForward:
     runs the forward on ``static_inputs[k]`` without the staging copy that ``self(x)`` makes."""
 
     def __init__(self, net, example_x: torch.Tensor, first_stream: int = 0, warmup: int = 2, post=None,
-                 static_inputs=None):
+                 static_inputs=None, ws_slot: int = 0):
         """post(logits, kl) -> outputs is captured behind the forward (e.g. the multi-GPU combine with
-        its NCCL all-reduce), so a whole step is one graph launch."""
+        its NCCL all-reduce), so a whole step is one graph launch.  ``ws_slot``: graphs that will be replayed
+        concurrently on different streams need different slots (functional.workspace_slot) and keep warmup > 0,
+        so that their private layer workspaces are created before the capture."""
         assert example_x.is_cuda
         self.net = net
         dev = example_x.device
@@ -39,7 +41,7 @@ class GraphedForward:
         self.first_stream = int(first_stream)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side), torch.no_grad():
+        with torch.cuda.stream(side), torch.no_grad(), Fn.workspace_slot(ws_slot):
             for _ in range(warmup):
                 with Fn.stream_base(self.base):
                     out = net(self.x)
@@ -51,7 +53,7 @@ class GraphedForward:
         for xin in self.inputs:
             graph = torch.cuda.CUDAGraph()
             n0 = _lib.launch_count()
-            with torch.cuda.graph(graph), torch.no_grad():
+            with torch.cuda.graph(graph), torch.no_grad(), Fn.workspace_slot(ws_slot):
                 Fn.noise_advance(self.base, _STRIDE)
                 with Fn.stream_base(self.base):
                     out = net(xin)

@@ -24,3 +24,8 @@ run "PREP_CARVEOUT=0" BBB_B200_PREP_CARVEOUT=0
 echo "== per-step trace of the tap-GEMMs (default, then SQ)"
 timeout 100 python tools/trace_tapgemm.py lrt 2>&1 | grep "^layer\|mma_full" | cut -c1-240
 BBB_B200_SQ_ONCHIP=1 timeout 100 python tools/trace_tapgemm.py lrt 2>&1 | grep "^layer\|mma_full" | cut -c1-240
+echo "== forwards in flight on S streams (bench.py --streams): headline vs S-stream figure"
+for S in 2 3; do
+  timeout 200 python bench.py --streams $S --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('S=$S headline', round(d['ms_per_step']*1e3,1), 'us', round(d['value']), ' streams', d['streams'] and (round(d['streams']['ms_per_step']*1e3,1), round(d['streams']['value'])))"
+done
