@@ -141,3 +141,26 @@ def test_fused_planner_matches_reference_child_lists():
     # fp32 math is never fused
     na = BBBAlexNet(10, 3, CFG_PRIORS)
     assert fused.plan(list(na.children()), (8, 3, 32, 32)) is None
+
+
+def test_workspace_slot_context_nests_and_restores():
+    """Layer workspaces are keyed per slot so that forwards replayed concurrently on different streams never
+    share prepared operand tiles / KL counters (functional.workspace_slot, GraphedForward(ws_slot=...))."""
+    import inspect
+    from pytorch_bayesiancnn_b200 import functional as Fn
+    from pytorch_bayesiancnn_b200.graph import GraphedForward
+    assert Fn._ws_slot == 0
+    with Fn.workspace_slot(2):
+        assert Fn._ws_slot == 2
+        with Fn.workspace_slot(5):
+            assert Fn._ws_slot == 5
+        assert Fn._ws_slot == 2
+    assert Fn._ws_slot == 0
+    try:
+        with Fn.workspace_slot(3):
+            raise RuntimeError("boom")
+    except RuntimeError:
+        pass
+    assert Fn._ws_slot == 0
+    sig = inspect.signature(GraphedForward.__init__).parameters
+    assert "static_inputs" in sig and "ws_slot" in sig and sig["ws_slot"].default == 0
