@@ -144,6 +144,12 @@ int bbb_layer_forward_fused(const bbb_layer_desc* desc,
                             uint64_t seed, uint64_t stream_id, const uint64_t* stream_base,
                             void* workspace, size_t workspace_bytes, void* cuda_stream);
 
+/* Host-only query (no GPU work, no GPU needed): would bbb_layer_forward_fused accept this layer with these layouts?
+ * Returns BBB_OK, or the error code the call would return (bbb_last_error() says why).  The host-side planner
+ * (fused.plan) asks before it commits a ModuleWrapper child list to the fused chain. */
+int bbb_fused_supported(const bbb_layer_desc* desc, int32_t in_layout, int32_t in_pitch, int32_t prev_hw,
+                        int32_t out_layout, int32_t out_pitch);
+
 /* Replaces layer.kl_loss() -> metrics.calculate_kl (metrics.py:27-29 with the call
  * binding of layers/BBB/BBBConv.py:80-82) when no forward preceded it: sigma is
  * recomputed from rho.  n_w = |W|, n_b = |bias| (0 if none). */

@@ -81,6 +81,7 @@ inline bool tc_supported(const bbb_layer_desc& d, const Geom& g) {
     if (g.M < 1 || g.N < 1) return false;
     if (tc_stages(g, 2) < 2) return false;
     if ((long)tc_npad(g) / TC_BN * (tc_kpad(g) / TC_BK) > 1 << 20) return false;
+    if (tc_npad(g) / TC_BN > 65535) return false;      // n tiles ride on gridDim.y
     return true;
 }
 
@@ -371,7 +372,7 @@ gemm_tc_kernel(const TcArgs p, const int stages) {
     float* xs = reinterpret_cast<float*>(sm + tiles_off + (size_t)stages * stage_bytes);   // staged input images (stage_x)
     __nv_bfloat16* xsh = reinterpret_cast<__nv_bfloat16*>(xs);
 
-    const int n_tile = blockIdx.x, m_tile = blockIdx.y;
+    const int n_tile = blockIdx.y, m_tile = blockIdx.x;     // M tiles on x: gridDim.x has no 65535 limit
     const int m0 = m_tile * TC_BM, n0 = n_tile * TC_BN;
     const int chw = g.Cin * g.HW;
     const int img0 = m0 / g.OHW;
@@ -663,7 +664,7 @@ inline cudaError_t launch_fwd_tc(TcArgs a, cudaStream_t st, int n_sm, int* n_lau
         if (2 * (smem + xs_elems * 4 + 1024) > per_sm && 2 * ((smem + xs_elems * 2 + 127) / 128 * 128 + 1024) <= per_sm) a.stage_x = 2;
         smem += xs_elems * (a.stage_x == 2 ? 2 : 4);
     }
-    dim3 grid(a.n_tiles, (g.M + TC_BM - 1) / TC_BM);
+    dim3 grid((g.M + TC_BM - 1) / TC_BM, a.n_tiles);
     cudaError_t e;
     if (lrt) {
         cudaFuncSetAttribute(gemm_tc_kernel<BBB_VARIANT_LRT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);

@@ -8,7 +8,10 @@ from __future__ import annotations
 
 import contextlib
 import ctypes as C
+import itertools
+import os
 import threading
+import weakref
 from typing import Iterable, Optional
 
 import torch
@@ -19,12 +22,47 @@ from . import _lib as L
 # --------------------------------------------------------------------------- #
 # noise bookkeeping (Python owns (seed, stream_id); kernels own the draws)
 # --------------------------------------------------------------------------- #
+_MASK64 = 0xFFFFFFFFFFFFFFFF
+_MC_NAMESPACE = 1 << 63            # stream ids of Monte-Carlo evaluation samples (mc_sample): disjoint from training's
+_instances = itertools.count()     # one _Noise per thread; the index keeps DataParallel replica threads apart
+
+
+def _rank() -> int:
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank()
+    except Exception:
+        pass
+    return int(os.environ.get("RANK", "0"))
+
+
 class _Noise(threading.local):
+    """(seed, stream counter) of the calling thread.
+
+    Default seed: derived from ``torch.initial_seed()``, the process rank and the thread's index, so that
+    ``torch.manual_seed(s)`` reseeds the engine like it reseeds the reference's CPU generator, and so that ranks /
+    DataParallel replica threads do not draw identical noise.  ``manual_seed`` pins an explicit seed instead
+    (same value on every rank = same noise on every rank, which is what MC sharding wants: see mc.py)."""
+
     def __init__(self):
-        self.seed = 0x5EEDB200
+        self.index = next(_instances)
+        self.explicit = False
+        self.seed = None
+        self.torch_seed = None
         self.counter = 0
         self.queue = None          # external-eps queue (parity mode)
         self.base = None           # device int64[1] stream base (CUDA-graph capture mode)
+
+    def current_seed(self) -> int:
+        if not self.explicit:
+            ts = torch.initial_seed()
+            if self.seed is None or ts != self.torch_seed:      # first use, or torch.manual_seed() was called since
+                self.torch_seed = ts
+                mix = (ts * 0x9E3779B97F4A7C15 + _rank() * 0xD1B54A32D192ED03 + self.index * 0x94D049BB133111EB
+                       + 0x5EEDB200) & _MASK64
+                self.seed, self.counter = mix, 0
+        return self.seed
 
 
 _noise = _Noise()
@@ -33,15 +71,39 @@ _noise = _Noise()
 def manual_seed(seed: int, counter: int = 0):
     """Seed the engine's Philox streams.  Every stochastic layer call consumes one
     stream id (counter += 1), so a fixed seed replays the same noise."""
-    _noise.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    _noise.explicit = True
+    _noise.seed = int(seed) & _MASK64
     _noise.counter = int(counter)
+
+
+def current_seed() -> int:
+    return _noise.current_seed()
 
 
 def begin_sample(sample_id: int):
     """Position the stream counter for Monte-Carlo sample `sample_id` (global id):
     layer calls of that sample use stream ids (sample_id << 32) + 0, 1, 2, ...  so
-    results do not depend on how samples are sharded over ranks."""
+    results do not depend on how samples are sharded over ranks.
+    Moves the calling thread's counter for good: prefer the ``mc_sample`` context manager,
+    which restores the training counter afterwards."""
     _noise.counter = int(sample_id) << 32
+
+
+@contextlib.contextmanager
+def mc_sample(sample_id: int, seed: Optional[int] = None):
+    """Layer calls inside draw Monte-Carlo evaluation sample `sample_id` (global id): stream ids
+    2^63 + (sample_id << 32) + 0, 1, 2, ... -- a namespace training never reaches, independent of how the samples
+    are sharded over ranks.  The thread's training counter (and seed) are restored on exit, so an evaluation pass
+    between epochs does not make training replay its noise."""
+    _noise.current_seed()
+    saved = (_noise.seed, _noise.counter, _noise.explicit)
+    if seed is not None:
+        _noise.seed, _noise.explicit = int(seed) & _MASK64, True
+    _noise.counter = _MC_NAMESPACE | (int(sample_id) << 32)
+    try:
+        yield
+    finally:
+        _noise.seed, _noise.counter, _noise.explicit = saved
 
 
 @contextlib.contextmanager
@@ -64,9 +126,21 @@ def noise_advance(base: torch.Tensor, inc: int):
 
 
 def next_stream() -> tuple[int, int]:
+    seed = _noise.current_seed()
     s = _noise.counter
     _noise.counter += 1
-    return _noise.seed, s
+    return seed, s
+
+
+def noise_snapshot():
+    """(counter, eps queue) -- lets a multi-layer caller roll the noise state back if it fails half-way."""
+    return _noise.counter, (list(_noise.queue) if _noise.queue is not None else None)
+
+
+def noise_restore(snap):
+    _noise.counter = snap[0]
+    if snap[1] is not None and _noise.queue is not None:
+        _noise.queue[:] = snap[1]
 
 
 @contextlib.contextmanager
@@ -118,7 +192,8 @@ def _require_cuda(t: torch.Tensor, what: str):
             "and has no CPU fallback")
 
 
-_ws_cache: dict = {}
+_ws_cache: dict = {}                              # shared scratch: (device, stream) -> buffer
+_ws_layer = weakref.WeakKeyDictionary()           # layer-private scratch: module -> {(device, slot): buffer}; dies with the layer
 _ws_slot = 0
 
 
@@ -138,16 +213,21 @@ def workspace_slot(k: int):
 def workspace(device, desc=None, owner=None) -> torch.Tensor:
     """Zero-initialised scratch.  Without `owner`: one per (device, stream) -- calls on
     one stream are ordered, so sharing is safe and the kernels leave the counters
-    zeroed.  With `owner` (a layer): a private buffer sized by bbb_workspace_bytes(desc),
-    which on the tcgen05 path also holds that layer's prepared bf16 operand tiles."""
+    zeroed.  With `owner` (a layer module): a private buffer sized by bbb_workspace_bytes(desc),
+    which on the tcgen05 path also holds that layer's prepared bf16 operand tiles; it is held
+    through a weak reference to the layer, so it is freed with it and never re-bound to another one."""
     n = int(L.lib().bbb_workspace_bytes(C.byref(desc) if desc is not None else None))
-    # a layer-private buffer is keyed by the layer only: zero-filled once, never re-created per stream/graph
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream if owner is None else None, owner,
-           _ws_slot if owner is not None else 0)
-    ws = _ws_cache.get(key)
+    if owner is None:
+        cache, key = _ws_cache, (device.index, torch.cuda.current_stream(device).cuda_stream)
+    else:
+        cache = _ws_layer.get(owner)
+        if cache is None:
+            cache = _ws_layer[owner] = {}
+        key = (device.index, _ws_slot)
+    ws = cache.get(key)
     if ws is None or ws.numel() < n:
         ws = torch.zeros(n, dtype=torch.uint8, device=device)
-        _ws_cache[key] = ws
+        cache[key] = ws
     return ws
 
 

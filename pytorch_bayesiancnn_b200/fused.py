@@ -112,7 +112,49 @@ def plan(children, x_shape):
         st.out_layout = L.LAYOUT_PACKED_BF16
         if st.out_chw[0] % 64:                  # tiled packed format: whole 64-channel blocks per pixel
             return None
+    # the engine has the last word (same checks bbb_layer_forward_fused makes, host-only): run() must not
+    # discover an unsupported shape after noise was drawn and prep kernels were enqueued on side streams
+    lib = L.lib()
+    for st in steps:
+        d = _step_desc(st, 0)
+        rc = lib.bbb_fused_supported(C.byref(d), st.in_layout, _in_pitch(st), st.prev_hw, st.out_layout, _out_pitch(st))
+        if rc == -2:                            # BBB_E_UNSUPPORTED: not fusable, the caller runs child by child
+            return None
+        L.check(rc, "bbb_fused_supported")
     return steps
+
+
+def _in_pitch(st):
+    cin, h, w = st.in_shape
+    return 0 if st.in_layout == L.LAYOUT_NCHW_F32 else cin * h * w
+
+
+def _out_pitch(st):
+    cout, oh, ow = st.out_chw
+    return cout * oh * ow if st.out_layout == L.LAYOUT_PACKED_BF16 else 0
+
+
+def _step_desc(st, phase):
+    m = st.layer
+    cin, h, w = st.in_shape
+    d = L.LayerDesc()
+    d.batch, d.in_channels, d.in_h, d.in_w = st.batch, cin, h, w
+    if st.linear:
+        d.out_channels, d.kernel_h, d.kernel_w = m.out_features, 1, 1
+        d.stride_h = d.stride_w = d.dil_h = d.dil_w = 1
+        d.pad_h = d.pad_w = 0
+    else:
+        (sh, sw), (ph, pw), (dh, dw) = st.conv
+        d.out_channels, d.kernel_h, d.kernel_w = m.out_channels, m.kernel_size[0], m.kernel_size[1]
+        d.stride_h, d.stride_w, d.pad_h, d.pad_w, d.dil_h, d.dil_w = sh, sw, ph, pw, dh, dw
+    d.variant, d.sample, d.has_bias = m._variant, 1, int(m.use_bias)     # ModuleWrapper calls children with sample=True
+    d.act_dtype, d.math = L.DTYPE_F32, L.MATH_BF16_TC
+    d.kl_convention = L.KL_BY_NAME[m.kl_convention]
+    d.epilogue_act = st.act
+    d.pool_k = d.pool_s = 2 if st.pool else 0
+    d.reserved[0] = phase
+    d.prior_mu, d.prior_sigma = float(m.prior_mu), float(m.prior_sigma)
+    return d
 
 
 _side_streams: dict = {}
@@ -147,37 +189,47 @@ def run(steps, x: torch.Tensor, overlap_prep: bool = True):
     depends on the preps only and runs on the side as well."""
     dev = x.device
     kls = torch.empty(len(steps), dtype=torch.float32, device=dev)
-    noise = [_draw_noise(st, x.shape[0], dev) for st in steps]
-    if overlap_prep:
-        main = torch.cuda.current_stream(dev)
-        chains = [_side_stream(dev, c) for c in range(min(_prep_chains(), len(steps)))]
-        for side in chains:
-            side.wait_stream(main)
-        events = []
-        for i, st in enumerate(steps):
-            side = chains[i % len(chains)]
-            with torch.cuda.stream(side):
-                run_step(st, None, None, None, 0, kl=kls[i], noise=noise[i], phase=L.FUSED_PREP_ONLY)
-                ev = torch.cuda.Event()
-                ev.record(side)
-                events.append(ev)
-        for side in chains[1:]:
-            chains[0].wait_stream(side)
-        with torch.cuda.stream(chains[0]):
-            kl_total = kls.sum()
-    cur, cur_sq, cur_pitch = x.contiguous().float(), None, 0
-    for i, st in enumerate(steps):
-        nxt = steps[i + 1].layer if i + 1 < len(steps) else None
+    snap = Fn.noise_snapshot()
+    main = torch.cuda.current_stream(dev)
+    chains = [_side_stream(dev, c) for c in range(min(_prep_chains(), len(steps)))] if overlap_prep else []
+    forked = False
+    try:
+        noise = [_draw_noise(st, x.shape[0], dev) for st in steps]
         if overlap_prep:
-            main.wait_event(events[i])
-            cur, cur_sq, cur_pitch = run_step(st, nxt, cur, cur_sq, cur_pitch, kl=kls[i], noise=noise[i],
-                                              phase=L.FUSED_SKIP_PREP)
-        else:
-            cur, cur_sq, cur_pitch = run_step(st, nxt, cur, cur_sq, cur_pitch, kl=kls[i], noise=noise[i])
-    if overlap_prep:
-        main.wait_stream(chains[0])        # joins every side stream (chain 0 waited for the others)
-    else:
-        kl_total = kls.sum()
+            for side in chains:
+                side.wait_stream(main)
+            forked = True
+            events = []
+            for i, st in enumerate(steps):
+                side = chains[i % len(chains)]
+                with torch.cuda.stream(side):
+                    run_step(st, None, None, None, 0, kl=kls[i], noise=noise[i], phase=L.FUSED_PREP_ONLY)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    events.append(ev)
+            for side in chains[1:]:
+                chains[0].wait_stream(side)
+            with torch.cuda.stream(chains[0]):
+                kl_total = kls.sum()
+        cur, cur_sq, cur_pitch = x.contiguous().float(), None, 0
+        for i, st in enumerate(steps):
+            nxt = steps[i + 1].layer if i + 1 < len(steps) else None
+            if overlap_prep:
+                main.wait_event(events[i])
+                cur, cur_sq, cur_pitch = run_step(st, nxt, cur, cur_sq, cur_pitch, kl=kls[i], noise=noise[i],
+                                                  phase=L.FUSED_SKIP_PREP)
+            else:
+                cur, cur_sq, cur_pitch = run_step(st, nxt, cur, cur_sq, cur_pitch, kl=kls[i], noise=noise[i])
+        if not overlap_prep:
+            kl_total = kls.sum()
+    except BaseException:
+        Fn.noise_restore(snap)                 # a retry / fallback sees the stream ids and eps queue it would have seen
+        raise
+    finally:
+        if forked:                             # ALWAYS re-join the forked side streams: `kls` and the layer workspaces are
+            for side in chains[1:]:            # written there, and an active graph capture must not be left with dangling forks
+                chains[0].wait_stream(side)
+            main.wait_stream(chains[0])
     return cur, kl_total
 
 
@@ -209,27 +261,9 @@ def run_step(st, nxt, cur, cur_sq, cur_pitch, kl=None, noise=None, phase=0):
     dev = m.W_mu.device
     B = st.batch                                    # (packed inputs carry rows padded to the 128-row tile)
     if True:
-        lrt = m._variant == L.VARIANT_LRT
-        stoch = True                                     # ModuleWrapper calls children with sample=True
         cin, h, w = st.in_shape
-        d = L.LayerDesc()
-        d.batch, d.in_channels, d.in_h, d.in_w = B, cin, h, w
+        d = _step_desc(st, phase)
         in_pitch = cur_pitch if st.in_layout == L.LAYOUT_NCHW_F32 else cin * h * w
-        if st.linear:
-            d.out_channels, d.kernel_h, d.kernel_w = m.out_features, 1, 1
-            d.stride_h = d.stride_w = d.dil_h = d.dil_w = 1
-            d.pad_h = d.pad_w = 0
-        else:
-            (sh, sw), (ph, pw), (dh, dw) = st.conv
-            d.out_channels, d.kernel_h, d.kernel_w = m.out_channels, m.kernel_size[0], m.kernel_size[1]
-            d.stride_h, d.stride_w, d.pad_h, d.pad_w, d.dil_h, d.dil_w = sh, sw, ph, pw, dh, dw
-        d.variant, d.sample, d.has_bias = m._variant, 1, int(m.use_bias)
-        d.act_dtype, d.math = L.DTYPE_F32, L.MATH_BF16_TC
-        d.kl_convention = L.KL_BY_NAME[m.kl_convention]
-        d.epilogue_act = st.act
-        d.pool_k = d.pool_s = 2 if st.pool else 0
-        d.reserved[0] = phase
-        d.prior_mu, d.prior_sigma = float(m.prior_mu), float(m.prior_sigma)
         cout, oh, ow = st.out_chw
         if phase == L.FUSED_PREP_ONLY:
             pitch, y, y_sq = cout * oh * ow if st.out_layout == L.LAYOUT_PACKED_BF16 else 0, None, None
@@ -247,7 +281,7 @@ def run_step(st, nxt, cur, cur_sq, cur_pitch, kl=None, noise=None, phase=0):
         if noise is None:
             noise = _draw_noise(st, B, dev)
         eps_a, eps_b, seed, stream_id, base = noise
-        ws = Fn.workspace(dev, d, id(m))
+        ws = Fn.workspace(dev, d, m)
         rc = lib.bbb_layer_forward_fused(
             C.byref(d), Fn._ptr(cur), Fn._ptr(cur_sq), st.in_layout, in_pitch, st.prev_hw,
             Fn._ptr(m.W_mu), Fn._ptr(m.W_rho), Fn._ptr(m.bias_mu), Fn._ptr(m.bias_rho),

@@ -9,7 +9,9 @@ models/BayesianModels/*.py import and train unchanged.  The bodies are new: one
 fused CUDA kernel per forward (through the C ABI), KL computed in that kernel.
 
 Engine knobs ride on ``set_flag`` (never on the constructor):
-  math           'fp32' | 'bf16' | 'auto'   arithmetic path (default from $BBB_B200_MATH or 'fp32')
+  math           'fp32' | 'bf16' | 'auto'   arithmetic path (default from $BBB_B200_MATH or 'auto': the tcgen05 tensor-core
+                                            path wherever the shape fits a UMMA tile, IEEE-fp32 CUDA cores otherwise;
+                                            'fp32' forces the exact-arithmetic kernels everywhere)
   kl_convention  'reference' | 'textbook'   default 'reference' = the formula as executed
 """
 from __future__ import annotations
@@ -32,7 +34,7 @@ _DEFAULT_PRIORS = {
 
 
 def _default_math() -> str:
-    return os.environ.get("BBB_B200_MATH", "fp32")
+    return os.environ.get("BBB_B200_MATH", "auto")
 
 
 def _default_fuse() -> bool:
@@ -146,8 +148,11 @@ class _BayesLayer(ModuleWrapper):
         return None
 
     def _versions(self):
+        """What a cached KL scalar depends on: the parameters' versions AND the KL settings (changing
+        kl_convention or the prior after a forward must not return the old value)."""
         ps = (self.W_mu, self.W_rho, self.bias_mu, self.bias_rho)
-        return tuple((p._version, p.data_ptr()) if p is not None else None for p in ps)
+        return tuple((p._version, p.data_ptr()) if p is not None else None for p in ps) + (
+            self.kl_convention, float(self.prior_mu), float(self.prior_sigma))
 
     def _cfg(self, sample):
         return {
@@ -159,7 +164,7 @@ class _BayesLayer(ModuleWrapper):
             "math": L.MATH_BY_NAME[self.math],
             "kl_convention": L.KL_BY_NAME[self.kl_convention],
             "act": L.ACT_NONE,
-            "owner": id(self),
+            "owner": self,
         }
 
     def forward(self, x, sample=True):
@@ -186,9 +191,17 @@ class _BayesLayer(ModuleWrapper):
         (BBB/BBBConv.py:64); kept as a read-only view for code that inspects it."""
         return torch.log1p(torch.exp(self.W_rho))
 
+    @W_sigma.setter
+    def W_sigma(self, value):
+        pass                                             # the reference assigns it in forward; derived here
+
     @property
     def bias_sigma(self):
         return torch.log1p(torch.exp(self.bias_rho)) if self.use_bias else None
+
+    @bias_sigma.setter
+    def bias_sigma(self, value):
+        pass
 
 
 class _ConvMixin:

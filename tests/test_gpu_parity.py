@@ -204,6 +204,7 @@ def test_full_size_properties_alexnet_b512(dev):
                         for m in net.modules() if hasattr(m, "W_mu"))
             assert abs(kl_sa - float(kla)) <= 1e-6 * abs(kl_sa)
             # deterministic path: a batch slice gives the same rows
+            net.set_flag("math", "fp32")
             net.eval()
             h = x
             h2 = x[:7]
@@ -306,7 +307,7 @@ def test_tc_model_cases_external_eps(golden_models, dev):
             logits, kl = net(c["x"].to(dev))
         e = scale_err(logits, c["logits"])
         print(name, "bf16 chain scale err", e)
-        assert e < 2 * BF16_TOL, (name, e)      # six bf16 layers chained; per-layer bar is 1e-2
+        assert e < BF16_TOL, (name, e)          # north_star bar: 1e-2 for the whole bf16 model (measured 4-8e-3)
         assert abs(float(kl) - float(c["kl"])) <= KL_TOL * abs(float(c["kl"])), (name, float(kl), float(c["kl"]))
 
 
@@ -360,7 +361,7 @@ def test_fused_chain_vs_oracle_external_eps(dev):
             assert net._fused_plans[(batch, 3, 32, 32)] is not None   # it really took the fused path
             e = scale_err(logits, ref)
             print("fused", variant, batch, classes, act, "scale err", e)
-            assert e < 2 * BF16_TOL, (variant, batch, e)
+            assert e < BF16_TOL, (variant, batch, e)
             assert abs(float(kl) - float(refkl)) <= KL_TOL * abs(float(refkl))
 
 
@@ -398,6 +399,7 @@ def _grad_case(dev, variant, conv, bias, use_philox):
         x = torch.randn(9, 37, generator=g)
         geom = None
     layer = layer.to(dev).train()
+    layer.set_flag("math", "fp32")
     P = [p.detach().cpu().clone().requires_grad_(True) if p is not None else None
          for p in (layer.W_mu, layer.W_rho, layer.bias_mu, layer.bias_rho)]
     xr = x.clone().requires_grad_(True)

@@ -138,8 +138,11 @@ def test_fused_planner_matches_reference_child_lists():
     net.__dict__["_fused_plans"] = {(8, 3, 32, 32): None}
     net.set_flag("math", "bf16")
     assert "_fused_plans" not in net.__dict__
-    # fp32 math is never fused
+    # the default math is 'auto' (tensor-core path where the shape fits): a plain drop-in user gets the fused chain;
+    # 'fp32' (exact-arithmetic CUDA-core kernels) is never fused
     na = BBBAlexNet(10, 3, CFG_PRIORS)
+    assert na.conv1.math == "auto" and fused.plan(list(na.children()), (8, 3, 32, 32)) is not None
+    na.set_flag("math", "fp32")
     assert fused.plan(list(na.children()), (8, 3, 32, 32)) is None
 
 

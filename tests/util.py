@@ -44,6 +44,7 @@ def build_layer_from_case(name, c, device):
         layer.W_mu.copy_(c["W_mu"]); layer.W_rho.copy_(c["W_rho"])
         if bias:
             layer.bias_mu.copy_(c["bias_mu"]); layer.bias_rho.copy_(c["bias_rho"])
+    layer.set_flag("math", "fp32")            # exact-arithmetic kernels unless the test asks for the tensor-core path
     return layer.to(device)
 
 
@@ -54,4 +55,5 @@ def load_params_into(net, params):
         for m, p in zip(layers, params):
             m.W_mu.copy_(p["W_mu"]); m.W_rho.copy_(p["W_rho"])
             m.bias_mu.copy_(p["bias_mu"]); m.bias_rho.copy_(p["bias_rho"])
+    net.set_flag("math", "fp32")                  # exact-arithmetic kernels unless the test asks for the tensor-core path
     return net
