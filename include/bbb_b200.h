@@ -205,6 +205,38 @@ int bbb_noise_advance(uint64_t* base, uint64_t inc, void* cuda_stream);
 int bbb_mc_combine(const float* logits, int32_t S, int32_t B, int32_t C,
                    float* log_outputs, float* moments, void* cuda_stream);
 
+/* Monte-Carlo combine + ELBO head + uncertainty outputs, FUSED with the one exchange of the forward path
+ * (main_bayesian.py:46-61, utils.py:14-22, metrics.py:12-14,23-24, uncertainty_estimation.py:70-96).
+ * The num_ens samples are sharded over `world` ranks (one process per GPU); this rank holds `S_local` of the
+ * `S_total` samples' logits [S_local, B, C].  One kernel: per-(image, class) partials of the local samples
+ * (the exact (max, sum-exp) pair of logmeanexp, + sum p / sum p^2 / sum logits with BBB_MC_MOMENTS) are stored straight
+ * into every rank's receive buffer over NVLink (peer-mapped memory, below), per-CTA release flags are raised, the
+ * peers' flags awaited, and the result finished locally in fixed rank order (bitwise identical on all ranks):
+ *   log_outputs [B,C] = logmeanexp_j log_softmax(logits_j)      kl_out = sum_j kl_j / S_total
+ *   pred / epistemic / aleatoric [B,C], entropy [B]             (nullable; need BBB_MC_MOMENTS)
+ *   head [4] = {nll*train_size + beta*kl, nll, accuracy, beta*kl}   (nullable; needs labels [B] int64)
+ * BBB_MC_NORMALIZED: p_hat = softplus(logits) / sum softplus (uncertainty_estimation.py:73-75) instead of softmax.
+ * peer_buffers: HOST array of `world` device pointers, one receive buffer per rank (bbb_mc_buffer_bytes each, zero-
+ *   filled once; [rank] is the local one; with world == 1 any device allocation will do);
+ * state: local device scratch of bbb_mc_state_bytes(), zero-filled once.  Sequence numbers inside make the buffers
+ * reusable call after call (and CUDA-graph replay after replay) with no reset.  Every rank must make the same calls. */
+enum { BBB_MC_MOMENTS = 1, BBB_MC_NORMALIZED = 2 };
+size_t bbb_mc_buffer_bytes(int32_t B, int32_t C, int32_t flags, int32_t world);
+size_t bbb_mc_state_bytes(void);
+int bbb_mc_exchange(const float* logits, int32_t S_local, int32_t S_total, int32_t B, int32_t C, const float* kl,
+                    int32_t flags, const int64_t* labels, float train_size, float beta, int32_t rank, int32_t world,
+                    void* const* peer_buffers, void* state, float* log_outputs, float* kl_out, float* pred,
+                    float* epistemic, float* aleatoric, float* entropy, float* head, void* cuda_stream);
+
+/* Peer-mapped receive buffers for bbb_mc_exchange (one process per GPU, same node): allocate locally, export a
+ * 64-byte CUDA-IPC handle, ship it to the peers by any host channel (the Python side uses torch.distributed),
+ * import theirs.  These five calls are the only ones in this library that allocate or synchronise. */
+int bbb_comm_alloc(size_t bytes, void** dev_ptr);            /* cudaMalloc + zero fill                 */
+int bbb_comm_free(void* dev_ptr);
+int bbb_comm_export(void* dev_ptr, void* handle64_host);     /* writes 64 bytes                        */
+int bbb_comm_import(const void* handle64_host, void** peer_ptr);
+int bbb_comm_unimport(void* peer_ptr);
+
 const char* bbb_last_error(void);
 int32_t bbb_abi_version(void);
 /* Number of kernels this library has launched since load (all entry points). */

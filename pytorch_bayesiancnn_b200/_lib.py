@@ -30,7 +30,10 @@ SYMBOLS = (
     "bbb_kl_forward",
     "bbb_kl_backward", "bbb_conv2d_backward", "bbb_linear_backward", "bbb_philox_normal_fill",
     "bbb_mc_combine", "bbb_noise_advance", "bbb_last_error", "bbb_abi_version", "bbb_launch_count",
+    "bbb_mc_buffer_bytes", "bbb_mc_state_bytes", "bbb_mc_exchange",
+    "bbb_comm_alloc", "bbb_comm_free", "bbb_comm_export", "bbb_comm_import", "bbb_comm_unimport",
 )
+MC_MOMENTS, MC_NORMALIZED = 1, 2
 
 
 class LayerDesc(C.Structure):
@@ -76,6 +79,20 @@ def _bind(lib):
     lib.bbb_philox_normal_fill.restype = C.c_int
     lib.bbb_mc_combine.argtypes = [fp, i32, i32, i32, fp, fp, vp]
     lib.bbb_mc_combine.restype = C.c_int
+    lib.bbb_mc_buffer_bytes.argtypes = [i32, i32, i32, i32]
+    lib.bbb_mc_buffer_bytes.restype = sz
+    lib.bbb_mc_state_bytes.argtypes = []
+    lib.bbb_mc_state_bytes.restype = sz
+    lib.bbb_mc_exchange.argtypes = [fp, i32, i32, i32, i32, fp, i32, vp, C.c_float, C.c_float, i32, i32,
+                                    C.POINTER(C.c_void_p), vp, fp, fp, fp, fp, fp, fp, fp, vp]
+    lib.bbb_mc_exchange.restype = C.c_int
+    lib.bbb_comm_alloc.argtypes = [sz, C.POINTER(C.c_void_p)]
+    lib.bbb_comm_export.argtypes = [vp, vp]
+    lib.bbb_comm_import.argtypes = [vp, C.POINTER(C.c_void_p)]
+    for name in ("bbb_comm_free", "bbb_comm_unimport"):
+        getattr(lib, name).argtypes = [vp]
+    for name in ("bbb_comm_alloc", "bbb_comm_free", "bbb_comm_export", "bbb_comm_import", "bbb_comm_unimport"):
+        getattr(lib, name).restype = C.c_int
     lib.bbb_noise_advance.argtypes = [vp, u64, vp]
     lib.bbb_noise_advance.restype = C.c_int
     lib.bbb_last_error.argtypes = []

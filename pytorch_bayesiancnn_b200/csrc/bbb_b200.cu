@@ -10,6 +10,8 @@
 #include "bwd_simt.cuh"
 #include "fwd_tc.cuh"
 #include "fused_tc.cuh"
+#include "conv_s4_tc.cuh"
+#include "mc_head.cuh"
 
 namespace {
 
@@ -151,8 +153,11 @@ size_t bbb_workspace_bytes(const bbb_layer_desc* desc) {
     if (!desc || desc->math == BBB_MATH_FP32) return kBaseWorkspace;
     bbb::Geom g;
     if (!bbb::make_geom(*desc, g)) return kBaseWorkspace;
-    const size_t a = bbb::tc_workspace_bytes(g), b = bbb::fused_workspace_bytes(g);
-    return kTcOffset + (a > b ? a : b);
+    size_t a = bbb::tc_workspace_bytes(g);
+    const size_t b = bbb::fused_workspace_bytes(g), c = bbb::conv_s4_workspace_bytes(g);
+    if (b > a) a = b;
+    if (c > a) a = c;
+    return kTcOffset + a;
 }
 
 int bbb_conv2d_forward(const bbb_layer_desc* desc, const void* x, const float* W_mu, const float* W_rho,
@@ -240,7 +245,24 @@ int bbb_layer_forward_fused(const bbb_layer_desc* d, const void* x, const void* 
     cudaStream_t st = (cudaStream_t)stream;
     const int out_mode = out_layout == BBB_LAYOUT_PACKED_BF16 ? 0 : (out_layout == BBB_LAYOUT_ROWMAJOR_F32 ? 1 : 2);
     int nl = 0;
-    if (in_layout == BBB_LAYOUT_NCHW_F32) {
+    static const bool s4_on = [] { const char* e = getenv("BBB_B200_CONV1_DIRECT"); return !(e && e[0] == '0'); }();
+    if (in_layout == BBB_LAYOUT_NCHW_F32 && s4_on && bbb::conv_s4_supported(*d, g, pool, out_mode == 0)) {
+        // stride-4 first layer: the tensor core reads its A operand straight from the staged image (conv_s4_tc.cuh)
+        bbb::S4Args a;
+        a.g = g; a.x = (const float*)x; a.w_mu = W_mu; a.w_rho = W_rho; a.b_mu = bias_mu; a.b_rho = bias_rho;
+        a.y = y; a.y_sq = y_sq; a.kl_out = kl_out; a.eps_a = eps_a; a.eps_b = eps_b;
+        a.key = bbb::make_key(seed, stream_id); a.stream_base = (const unsigned long long*)stream_base;
+        a.kl_counter = (unsigned int*)ws; a.kl_partials = (double*)((char*)ws + kCounterBytes);
+        a.prior_mu = d->prior_mu; a.prior_sigma = d->prior_sigma;
+        a.sample = d->sample; a.kl_convention = d->kl_convention; a.has_bias = d->has_bias; a.act = d->epilogue_act;
+        a.variant = d->variant; a.out_pitch = out_pitch;
+        a.wtiles = (__nv_bfloat16*)((char*)ws + kTcOffset);
+        a.bias_ws = (float*)((char*)ws + kTcOffset + (size_t)g.KH * 2 * bbb::S4_BPLANE);
+        a.trace = g_trace;
+        a.tl_prep = tl_slot(!skip_prep, "conv_s4_prep", g); a.tl_gemm = tl_slot(!prep_only, "conv_s4", g);
+        cudaError_t e = bbb::launch_conv_s4(a, st, !skip_prep, !prep_only, &nl);
+        if (e != cudaSuccess) return cuda_fail(e, "conv_s4 launch");
+    } else if (in_layout == BBB_LAYOUT_NCHW_F32) {
         bbb::TcArgs a;
         a.g = g; a.x = x; a.w_mu = W_mu; a.w_rho = W_rho; a.b_mu = bias_mu; a.b_rho = bias_rho;
         a.y = y; a.kl_out = kl_out; a.act_std = nullptr; a.eps_a = eps_a; a.eps_b = eps_b;
@@ -339,6 +361,81 @@ int bbb_mc_combine(const float* logits, int32_t S, int32_t B, int32_t C, float* 
     if (e != cudaSuccess) return cuda_fail(e, "mc_combine launch");
     g_launches += 1;
     return BBB_OK;
+}
+
+size_t bbb_mc_buffer_bytes(int32_t B, int32_t C, int32_t flags, int32_t world) {
+    if (B <= 0 || C <= 0 || world <= 0 || world > bbb::MCX_MAX_RANKS) return 0;
+    return bbb::mcx_buffer_bytes(B, C, flags & BBB_MC_MOMENTS, world);
+}
+size_t bbb_mc_state_bytes(void) { return 64 + (size_t)bbb::MCX_MAX_CTAS * 2 * sizeof(double); }
+
+int bbb_mc_exchange(const float* logits, int32_t S_local, int32_t S_total, int32_t B, int32_t C, const float* kl,
+                    int32_t flags, const int64_t* labels, float train_size, float beta, int32_t rank, int32_t world,
+                    void* const* peer_buffers, void* state, float* log_outputs, float* kl_out, float* pred,
+                    float* epistemic, float* aleatoric, float* entropy, float* head, void* cuda_stream) {
+    if (!log_outputs || !peer_buffers || !state) return fail(BBB_E_INVALID, "NULL pointer");
+    if (S_local < 0 || S_total <= 0 || B <= 0 || C <= 0) return fail(BBB_E_INVALID, "bad S/B/C");
+    if (S_local > 0 && !logits) return fail(BBB_E_INVALID, "S_local > 0 but logits is NULL");
+    if (S_local > bbb::MCX_MAX_SLOCAL) return fail(BBB_E_UNSUPPORTED, "more than %d local samples per call", bbb::MCX_MAX_SLOCAL);
+    if (world < 1 || world > bbb::MCX_MAX_RANKS || rank < 0 || rank >= world) return fail(BBB_E_INVALID, "bad rank/world %d/%d", rank, world);
+    if ((pred || epistemic || aleatoric || entropy) && !(flags & BBB_MC_MOMENTS))
+        return fail(BBB_E_INVALID, "uncertainty outputs need BBB_MC_MOMENTS");
+    bbb::McxArgs a;
+    a.logits = logits; a.kl = kl; a.S_local = S_local; a.S_total = S_total; a.B = B; a.C = C;
+    a.want_moments = (flags & BBB_MC_MOMENTS) ? 1 : 0; a.normalized = (flags & BBB_MC_NORMALIZED) ? 1 : 0;
+    a.labels = (const long long*)labels; a.train_size = train_size; a.beta = beta; a.rank = rank; a.world = world;
+    for (int q = 0; q < bbb::MCX_MAX_RANKS; ++q) a.peer[q] = q < world ? (unsigned char*)peer_buffers[q] : nullptr;
+    for (int q = 0; q < world; ++q) if (!a.peer[q]) return fail(BBB_E_INVALID, "peer buffer %d is NULL", q);
+    a.seq = (unsigned int*)state; a.done = (unsigned int*)state + 1; a.timeouts = (unsigned int*)state + 2;
+    a.timeout_ns = 10ull * 1000 * 1000 * 1000;
+    if (const char* e = getenv("BBB_B200_MC_TIMEOUT_MS")) a.timeout_ns = (unsigned long long)atoll(e) * 1000000ull;
+    a.head_partials = (double*)((char*)state + 64);
+    a.log_outputs = log_outputs; a.kl_out = kl_out; a.pred = pred; a.epistemic = epistemic; a.aleatoric = aleatoric;
+    a.entropy = entropy; a.head = head;
+    // the grid depends on B only: CTA c of every rank owns the same images, so flags pair up CTA by CTA.  At most
+    // MCX_MAX_CTAS CTAs: all co-resident, so a CTA spinning on a peer's flag never keeps that peer's producer off an SM.
+    int grid = (B + bbb::MCX_THREADS / 32 - 1) / (bbb::MCX_THREADS / 32);
+    if (grid > bbb::MCX_MAX_CTAS) grid = bbb::MCX_MAX_CTAS;
+    bbb::mc_exchange_kernel<<<grid, bbb::MCX_THREADS, 0, (cudaStream_t)cuda_stream>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "mc_exchange launch");
+    g_launches += 1;
+    return BBB_OK;
+}
+
+int bbb_comm_alloc(size_t bytes, void** dev_ptr) {
+    if (!dev_ptr || bytes == 0) return fail(BBB_E_INVALID, "bad arguments");
+    cudaError_t e = cudaMalloc(dev_ptr, bytes);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    e = cudaMemset(*dev_ptr, 0, bytes);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemset");
+    e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceSynchronize");
+    return BBB_OK;
+}
+int bbb_comm_free(void* dev_ptr) {
+    cudaError_t e = cudaFree(dev_ptr);
+    return e == cudaSuccess ? BBB_OK : cuda_fail(e, "cudaFree");
+}
+int bbb_comm_export(void* dev_ptr, void* handle64_host) {
+    if (!dev_ptr || !handle64_host) return fail(BBB_E_INVALID, "NULL pointer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, dev_ptr);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaIpcGetMemHandle");
+    memcpy(handle64_host, &h, 64);
+    return BBB_OK;
+}
+int bbb_comm_import(const void* handle64_host, void** peer_ptr) {
+    if (!handle64_host || !peer_ptr) return fail(BBB_E_INVALID, "NULL pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64_host, 64);
+    cudaError_t e = cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    return e == cudaSuccess ? BBB_OK : cuda_fail(e, "cudaIpcOpenMemHandle");
+}
+int bbb_comm_unimport(void* peer_ptr) {
+    cudaError_t e = cudaIpcCloseMemHandle(peer_ptr);
+    return e == cudaSuccess ? BBB_OK : cuda_fail(e, "cudaIpcCloseMemHandle");
 }
 
 int bbb_noise_advance(uint64_t* base, uint64_t inc, void* cuda_stream) {

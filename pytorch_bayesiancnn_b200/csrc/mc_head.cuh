@@ -1,0 +1,217 @@
+// Monte-Carlo combine + ELBO head + uncertainty outputs, fused with the ONE exchange of the forward path.
+//
+// What sits directly above the Bayesian layers:
+//   main_bayesian.py:46-53   outputs[:,:,j] = log_softmax(net(x)); log_outputs = logmeanexp_j; kl = mean_j kl_j
+//   utils.py:14-22           logmeanexp
+//   metrics.py:12-14,23-24   ELBO = nll_loss(log_outputs, y, mean) * train_size + beta * kl ; acc
+//   uncertainty_estimation.py:70-96   p_hat = softmax (or softplus-normalised, :73-77); pred = mean_t logits;
+//                            epistemic = diag((p_hat - p_bar)^T (p_hat - p_bar)) / T; aleatoric = diag(diag(p_bar) - p_hat^T p_hat / T)
+//
+// The num_ens samples are sharded over ranks (one process per GPU).  Every rank reduces ITS samples to per-(image,
+// class) partials, pushes them straight into every peer's receive buffer over NVLink (plain st.global on peer-mapped
+// memory obtained through CUDA IPC), raises a per-CTA flag with release semantics, waits for the peers' flags, and
+// finishes the reduction + head locally -- one kernel, no NCCL, no host round trip.  The partials are the exact
+// (max, sum-exp) pairs of logmeanexp, so the result equals the reference's logmeanexp even where every sample's
+// probability underflows (a plain sum of softmaxes does not).
+//
+// Receive buffer of one rank (all ranks use the same layout):
+//   [0, 4096)                       control: u32 flags[world <= 16][MCX_MAX_CTAS]  (value = sequence number delivered)
+//   [4096, ...)                     float data[2 slots][world][n_planes * B * C + 2]
+// Sequence numbers make the buffer reusable without a reset: launch k of a rank uses slot k & 1 and waits for flag
+// values >= k; a peer can be at most one launch ahead (it cannot finish launch k+1 before it has OUR launch k+1 flags).
+#pragma once
+#include "common.cuh"
+
+namespace bbb {
+
+constexpr int MCX_MAX_RANKS = 16, MCX_MAX_CTAS = 64, MCX_CTRL_BYTES = 4096, MCX_THREADS = 256, MCX_MAX_SLOCAL = 256;
+
+struct McxArgs {
+    const float* logits;          // [S_local, B, C] this rank's samples
+    const float* kl;              // device scalar: the KL of ONE sample (identical for every sample); nullable
+    int S_local, S_total, B, C;
+    int want_moments, normalized; // moments: also exchange sum p, sum p^2, sum logits;  normalized: p_hat = softplus/sum softplus
+    const long long* labels;      // [B] int64, nullable
+    float train_size, beta;
+    int rank, world;
+    unsigned char* peer[MCX_MAX_RANKS];   // receive buffers; peer[rank] is the local one
+    unsigned int* seq;            // local device counter: launches completed so far
+    unsigned int* done;           // local device counter (zeroed once): CTAs finished in this launch
+    unsigned int* timeouts;       // local device counter: waits that gave up (a peer never delivered) -- results are then invalid
+    unsigned long long timeout_ns;
+    double* head_partials;        // [MCX_MAX_CTAS][2] nll sum, correct count
+    // outputs (local)
+    float* log_outputs;           // [B, C]
+    float* kl_out;                // scalar: sum_j kl_j / S_total
+    float* pred; float* epistemic; float* aleatoric; float* entropy;   // [B,C] x3, [B]; nullable (need want_moments)
+    float* head;                  // [4]: loss, nll, accuracy, beta*kl; nullable (needs labels)
+};
+
+__host__ __device__ inline int mcx_planes(int want_moments) { return want_moments ? 5 : 2; }
+__host__ __device__ inline size_t mcx_rank_floats(int B, int C, int want_moments) { return (size_t)mcx_planes(want_moments) * B * C + 2; }
+__host__ inline size_t mcx_buffer_bytes(int B, int C, int want_moments, int world) {
+    return MCX_CTRL_BYTES + 2 * (size_t)world * mcx_rank_floats(B, C, want_moments) * sizeof(float);
+}
+
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float softplus_f(float v) { return v > 20.0f ? v : log1pf(expf(v)); }   // F.softplus(beta=1, threshold=20)
+
+__global__ void __launch_bounds__(MCX_THREADS)
+mc_exchange_kernel(const McxArgs p) {
+    __shared__ float norm_s[MCX_THREADS / 32][MCX_MAX_SLOCAL];   // per warp: log-sum-exp (or softplus sum) of each local sample's row
+    __shared__ unsigned int seq_sh;
+    __shared__ double red[32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = MCX_THREADS / 32;
+    const int B = p.B, C = p.C, BC = B * C;
+    const int rows_per_cta = (B + gridDim.x - 1) / gridDim.x;
+    const int b0 = blockIdx.x * rows_per_cta, b1 = min(B, b0 + rows_per_cta);
+    if (threadIdx.x == 0) seq_sh = *p.seq + 1u;
+    __syncthreads();
+    const unsigned int seq = seq_sh;
+    const size_t rank_floats = mcx_rank_floats(B, C, p.want_moments);
+    const size_t slot_off = (size_t)(seq & 1u) * p.world * rank_floats;     // in floats, behind the control block
+    const float inv_S = 1.0f / (float)p.S_total;
+
+    // ---- (1) local partials of this CTA's images, pushed to every rank's receive buffer ---------------------
+    for (int b = b0 + warp; b < b1; b += nwarp) {
+        for (int s = 0; s < p.S_local; ++s) {                   // row normaliser of every local sample
+            const float* row = p.logits + ((size_t)s * B + b) * C;
+            float r;
+            if (p.normalized) {
+                float acc = 0.0f;
+                for (int c = lane; c < C; c += 32) acc += softplus_f(row[c]);
+                r = warp_sum(acc);
+            } else {
+                float mx = -INFINITY;
+                for (int c = lane; c < C; c += 32) mx = fmaxf(mx, row[c]);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                float se = 0.0f;
+                for (int c = lane; c < C; c += 32) se += expf(row[c] - mx);
+                r = mx + logf(warp_sum(se));
+            }
+            if (lane == 0) norm_s[warp][s] = r;
+        }
+        __syncwarp();
+        for (int c = lane; c < C; c += 32) {
+            float mx = -INFINITY, acc = 0.0f, sp = 0.0f, sp2 = 0.0f, sl = 0.0f;
+            for (int s = 0; s < p.S_local; ++s) {
+                const float l = p.logits[((size_t)s * B + b) * C + c];
+                float pr, lp;
+                if (p.normalized) { pr = softplus_f(l) / norm_s[warp][s]; lp = logf(pr); }
+                else { lp = l - norm_s[warp][s]; pr = expf(lp); }            // log_softmax (main_bayesian.py:49)
+                if (lp > mx) { acc = acc * expf(mx - lp) + 1.0f; mx = lp; }  // online logsumexp over the samples
+                else acc += expf(lp - mx);
+                sp += pr; sp2 += pr * pr; sl += l;
+            }
+            const size_t e = (size_t)b * C + c;
+            for (int q = 0; q < p.world; ++q) {
+                float* dst = reinterpret_cast<float*>(p.peer[q] + MCX_CTRL_BYTES) + slot_off + (size_t)p.rank * rank_floats;
+                dst[e] = mx; dst[BC + e] = acc;
+                if (p.want_moments) { dst[2 * (size_t)BC + e] = sp; dst[3 * (size_t)BC + e] = sp2; dst[4 * (size_t)BC + e] = sl; }
+            }
+        }
+        __syncwarp();
+    }
+    if (blockIdx.x == 0 && threadIdx.x < p.world) {             // this rank's KL contribution: S_local * kl
+        float* dst = reinterpret_cast<float*>(p.peer[threadIdx.x] + MCX_CTRL_BYTES) + slot_off + (size_t)p.rank * rank_floats;
+        dst[(size_t)mcx_planes(p.want_moments) * BC] = p.kl ? (float)p.S_local * __ldg(p.kl) : 0.0f;
+    }
+    __syncthreads();
+    // ---- (2) publish: everything this CTA stored is visible system-wide before the flag is ----------------
+    if (threadIdx.x == 0) __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < p.world) {
+        unsigned int* flags = reinterpret_cast<unsigned int*>(p.peer[threadIdx.x]);
+        st_release_sys(flags + p.rank * MCX_MAX_CTAS + blockIdx.x, seq);
+    }
+    // ---- (3) wait for the same CTA of every peer ---------------------------------------------------------
+    if (threadIdx.x < p.world) {
+        const unsigned int* f = reinterpret_cast<const unsigned int*>(p.peer[p.rank]) + threadIdx.x * MCX_MAX_CTAS + blockIdx.x;
+        const unsigned long long t0 = globaltimer_ns();
+        while ((int)(ld_acquire_sys(f) - seq) < 0) {
+            __nanosleep(20);
+            if (globaltimer_ns() - t0 > p.timeout_ns) { atomicAdd(p.timeouts, 1u); break; }   // never hang the GPU on a lost peer
+        }
+    }
+    __syncthreads();
+    // ---- (4) finish: fixed rank order => bitwise identical on every rank ----------------------------------
+    const float* rx = reinterpret_cast<const float*>(p.peer[p.rank] + MCX_CTRL_BYTES) + slot_off;
+    double nll_acc = 0.0, hit_acc = 0.0;
+    for (int b = b0 + warp; b < b1; b += nwarp) {
+        float best = -INFINITY; int best_c = 0x7fffffff;
+        float ent = 0.0f, lab_lp = 0.0f;
+        const long long lab = p.labels ? p.labels[b] : -1;
+        for (int c = lane; c < C; c += 32) {
+            const size_t e = (size_t)b * C + c;
+            float M = -INFINITY;
+            for (int q = 0; q < p.world; ++q) M = fmaxf(M, __ldcg(rx + (size_t)q * rank_floats + e));
+            float tot = 0.0f, sp = 0.0f, sp2 = 0.0f, sl = 0.0f;
+            for (int q = 0; q < p.world; ++q) {
+                const float* r = rx + (size_t)q * rank_floats;
+                const float mq = __ldcg(r + e), aq = __ldcg(r + BC + e);
+                if (aq > 0.0f) tot += aq * expf(mq - M);
+                if (p.want_moments) { sp += __ldcg(r + 2 * (size_t)BC + e); sp2 += __ldcg(r + 3 * (size_t)BC + e); sl += __ldcg(r + 4 * (size_t)BC + e); }
+            }
+            const float lo = M + logf(tot * inv_S);                       // utils.py:14-22
+            p.log_outputs[e] = lo;
+            if (lo > best) { best = lo; best_c = c; }
+            if ((long long)c == lab) lab_lp = lo;
+            if (p.want_moments) {
+                const float pbar = sp * inv_S, p2 = sp2 * inv_S;
+                if (p.pred) p.pred[e] = sl * inv_S;                       // uncertainty_estimation.py:82-83
+                if (p.epistemic) p.epistemic[e] = p2 - pbar * pbar;       // :89-91  (E[p^2] - p_bar^2)
+                if (p.aleatoric) p.aleatoric[e] = pbar - p2;              // :94-95  (p_bar - E[p^2])
+                ent -= pbar > 0.0f ? pbar * logf(pbar) : 0.0f;            // H[p_bar] (no reference)
+            }
+        }
+        // row reductions: entropy, the label's log-probability, argmax (first maximal class, like torch.argmax on ties)
+        ent = warp_sum(ent); lab_lp = warp_sum(lab_lp);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+            if (ob > best || (ob == best && oc < best_c)) { best = ob; best_c = oc; }
+        }
+        if (lane == 0) {
+            if (p.entropy && p.want_moments) p.entropy[b] = ent;
+            if (p.labels) { nll_acc -= (double)lab_lp; hit_acc += (best_c == (int)lab) ? 1.0 : 0.0; }
+        }
+    }
+    // ---- (5) cross-CTA finish (deterministic order), KL, ELBO head, sequence number ------------------------
+    const double nll_cta = block_sum(nll_acc, red);
+    __syncthreads();
+    const double hit_cta = block_sum(hit_acc, red);
+    if (threadIdx.x == 0) {
+        p.head_partials[2 * blockIdx.x] = nll_cta; p.head_partials[2 * blockIdx.x + 1] = hit_cta;
+        __threadfence();
+        const unsigned int prev = atomicAdd(p.done, 1u);
+        if (prev == gridDim.x - 1) {
+            __threadfence();
+            float klsum = 0.0f;
+            for (int q = 0; q < p.world; ++q) klsum += __ldcg(rx + (size_t)q * rank_floats + (size_t)mcx_planes(p.want_moments) * BC);
+            const float kl = klsum * inv_S;                               // main_bayesian.py:51  (kl / num_ens)
+            if (p.kl_out) *p.kl_out = kl;
+            if (p.head && p.labels) {
+                double nll = 0.0, hit = 0.0;
+                for (unsigned int i = 0; i < gridDim.x; ++i) { nll += ((volatile double*)p.head_partials)[2 * i]; hit += ((volatile double*)p.head_partials)[2 * i + 1]; }
+                const float nllf = (float)(nll / (double)B);              // F.nll_loss(..., reduction='mean')
+                p.head[0] = nllf * p.train_size + p.beta * kl;            // metrics.py:14
+                p.head[1] = nllf;
+                p.head[2] = (float)(hit / (double)B);                     // metrics.py:23-24
+                p.head[3] = p.beta * kl;
+            }
+            *p.done = 0u;
+            *p.seq = seq;
+        }
+    }
+}
+
+}  // namespace bbb

@@ -92,14 +92,14 @@ def begin_sample(sample_id: int):
 @contextlib.contextmanager
 def mc_sample(sample_id: int, seed: Optional[int] = None):
     """Layer calls inside draw Monte-Carlo evaluation sample `sample_id` (global id): stream ids
-    2^63 + (sample_id << 32) + 0, 1, 2, ... -- a namespace training never reaches, independent of how the samples
-    are sharded over ranks.  The thread's training counter (and seed) are restored on exit, so an evaluation pass
+    2^63 + (sample_id << 40) + 0, 1, 2, ... (2^40 ids per sample: room for 2^20 CUDA-graph replays of 2^20 layer calls)
+    -- a namespace training never reaches, independent of how the samples are sharded over ranks.  The thread's training counter (and seed) are restored on exit, so an evaluation pass
     between epochs does not make training replay its noise."""
     _noise.current_seed()
     saved = (_noise.seed, _noise.counter, _noise.explicit)
     if seed is not None:
         _noise.seed, _noise.explicit = int(seed) & _MASK64, True
-    _noise.counter = _MC_NAMESPACE | (int(sample_id) << 32)
+    _noise.counter = _MC_NAMESPACE | (int(sample_id) << 40)
     try:
         yield
     finally:

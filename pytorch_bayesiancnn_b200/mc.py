@@ -1,20 +1,30 @@
-"""Monte-Carlo sample sharding and the one exchange of the forward path.
+"""Monte-Carlo sample sharding, the one exchange of the forward path, and the heads above it.
 
-The reference's ``num_ens`` loop (main_bayesian.py:46-53, validate :75-80;
-uncertainty_estimation.py:70-78) runs S independent weight samples of the SAME batch and
-combines them with logmeanexp of log-softmax.  Samples only differ in their noise, so
-rank r of R takes the global sample ids {j : j mod R == r} (Philox stream ``j << 32``:
-results do not depend on R) and ONE all-reduce of [3*B*C + 1] floats carries
-sum_j softmax_j, sum_j softmax_j^2, sum_j logits_j and sum_j KL_j.
+The reference's ``num_ens`` loop (main_bayesian.py:46-53, validate :75-80; uncertainty_estimation.py:70-78) runs S
+independent weight samples of the SAME batch and combines them with logmeanexp of log-softmax.  Samples only differ in
+their noise, so rank r of R takes the global sample ids {j : j mod R == r} (Philox stream namespace of sample j:
+results do not depend on R) and ONE exchange carries the per-(image, class) partials and the KL.
 
-``forward_fn(x, sample_id) -> (logits [B,C], kl scalar)`` is whatever runs one sample
-(the CUDA engine in production; tests drive the host logic with a CPU stand-in over gloo).
+Two implementations of the same contract:
+
+* ``MCForward`` / ``mc_forward(net, ...)`` -- the product path on the CUDA engine: the local samples run through the
+  engine (fused tcgen05 chain where the net allows), then ONE kernel (``bbb_mc_exchange``, csrc/mc_head.cuh) reduces
+  them, pushes the partials into every peer's receive buffer over NVLink (CUDA-IPC peer-mapped memory, no NCCL on the
+  data path), waits for the peers and finishes logmeanexp, KL/num_ens, the ELBO head (metrics.py:12-14, 23-24) and the
+  uncertainty outputs (uncertainty_estimation.py:80-96, softmax or softplus-normalised :73-77) on the device.  The whole
+  step is one captured CUDA graph.
+* ``mc_forward(forward_fn, ...)`` with a plain callable -- backend-agnostic host logic on torch.distributed (gloo on
+  CPU in the tests): same sharding, same exact (max, sum-exp) partials, one all-gather.
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import Callable, Optional
 
 import torch
+
+from . import _lib as L
+from . import functional as Fn
 
 
 def local_samples(num_ens: int, world: int, rank: int):
@@ -22,48 +32,265 @@ def local_samples(num_ens: int, world: int, rank: int):
     return list(range(rank, num_ens, world))
 
 
-def mc_forward(forward_fn: Callable, x: torch.Tensor, num_ens: int, group=None, want_uncertainty: bool = False):
-    """Returns (log_outputs [B,C], kl) like main_bayesian.py:46-53, and optionally
-    (pred, epistemic, aleatoric, entropy) like uncertainty_estimation.py:70-96."""
+def get_beta(batch_idx, m, beta_type, epoch=None, num_epochs=None):
+    """metrics.py:32-46 (host scalar; it only feeds the `beta` argument of the ELBO head)."""
+    if isinstance(beta_type, (int, float)):
+        return float(beta_type)
+    if beta_type == "Blundell":
+        return 2 ** (m - (batch_idx + 1)) / (2 ** m - 1)
+    if beta_type == "Soenderby":
+        if epoch is None or num_epochs is None:
+            raise ValueError("Soenderby method requires both epoch and num_epochs to be passed.")
+        return min(epoch / (num_epochs // 4), 1)
+    if beta_type == "Standard":
+        return 1 / m
+    return 0
+
+
+def _dist_info(group):
     import torch.distributed as dist
-    distributed = dist.is_available() and dist.is_initialized()
-    world = dist.get_world_size(group) if distributed else 1
-    rank = dist.get_rank(group) if distributed else 0
-    acc = None
-    for j in local_samples(num_ens, world, rank):
+    on = dist.is_available() and dist.is_initialized()
+    return (dist if on else None), (dist.get_world_size(group) if on else 1), (dist.get_rank(group) if on else 0)
+
+
+class MCForward:
+    """``out = MCForward(net, example_x, num_ens, ...)(x, labels=None)`` -- the sharded MC step on the engine.
+
+    Returns a dict of device tensors (the same objects every call; identical on all ranks):
+      log_outputs [B,C], kl (= sum_j kl_j / num_ens), and with ``want_uncertainty`` pred / epistemic / aleatoric [B,C]
+      and entropy [B]; with ``with_labels`` head = [loss, nll, accuracy, beta*kl] (metrics.py:12-14, 23-24).
+    """
+
+    def __init__(self, net, example_x: torch.Tensor, num_ens: int, group=None, want_uncertainty: bool = False,
+                 normalized: bool = False, with_labels: bool = False, train_size: float = 1.0, beta: float = 0.0,
+                 seed: Optional[int] = None, graph: bool = True, num_classes: Optional[int] = None):
+        Fn._require_cuda(example_x, "MCForward")
+        lib = L.lib()
+        self.net, self.group = net, group
+        self.dist, self.world, self.rank = _dist_info(group)
+        if self.world > 16:
+            raise L.EngineError("MCForward: at most 16 ranks (one node)")
+        dev = self.dev = example_x.device
+        self.num_ens = int(num_ens)
+        self.ids = local_samples(self.num_ens, self.world, self.rank)
+        self.B = int(example_x.shape[0])
+        self.C = int(num_classes if num_classes is not None else net.num_classes)
+        self.flags = (L.MC_MOMENTS if want_uncertainty else 0) | (L.MC_NORMALIZED if normalized else 0)
+        self.want_uncertainty, self.with_labels = want_uncertainty, with_labels
+        self.train_size, self.beta = float(train_size), float(beta)
+        # every rank must draw sample j from the same (seed, stream): share rank 0's seed unless one is given
+        if seed is None:
+            box = [Fn.current_seed()]
+            if self.world > 1:
+                self.dist.broadcast_object_list(box, src=self.dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            seed = box[0]
+        self.seed = int(seed)
+        B, Cc = self.B, self.C
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.x = example_x.clone()
+        self.labels = torch.zeros(B, dtype=torch.int64, device=dev) if with_labels else None
+        self.logits = torch.zeros(max(1, len(self.ids)), B, Cc, **f32)
+        self.kl_one = torch.zeros((), **f32)
+        self.out = {"log_outputs": torch.empty(B, Cc, **f32), "kl": torch.empty((), **f32)}
+        if want_uncertainty:
+            for k in ("pred", "epistemic", "aleatoric"):
+                self.out[k] = torch.empty(B, Cc, **f32)
+            self.out["entropy"] = torch.empty(B, **f32)
+        if with_labels:
+            self.out["head"] = torch.empty(4, **f32)
+        self.state = torch.zeros(int(lib.bbb_mc_state_bytes()), dtype=torch.uint8, device=dev)
+        nbytes = int(lib.bbb_mc_buffer_bytes(B, Cc, self.flags, self.world))
+        self._imported, self._own = [], None
+        if self.world == 1:
+            self._buf = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+            ptrs = [self._buf.data_ptr()]
+        else:
+            ptrs = self._open_peers(nbytes)
+        self.peers = (C.c_void_p * self.world)(*ptrs)
+        self.base = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.graph = None
+        self.replays = 0
+        self.kernels_per_step = None
+        if graph:
+            self._capture()
+
+    # -- peer-mapped receive buffers (CUDA IPC; handles travel over torch.distributed) -----------------------
+    def _open_peers(self, nbytes):
+        lib = L.lib()
+        torch.cuda.synchronize(self.dev)
+        own = C.c_void_p()
+        with torch.cuda.device(self.dev):
+            L.check(lib.bbb_comm_alloc(C.c_size_t(nbytes), C.byref(own)), "bbb_comm_alloc")
+            self._own = own.value
+            handle = (C.c_ubyte * 64)()
+            L.check(lib.bbb_comm_export(C.c_void_p(self._own), handle), "bbb_comm_export")
+            handles = [None] * self.world
+            self.dist.all_gather_object(handles, bytes(handle), group=self.group)
+            ptrs = []
+            for q, h in enumerate(handles):
+                if q == self.rank:
+                    ptrs.append(self._own)
+                    continue
+                peer = C.c_void_p()
+                L.check(lib.bbb_comm_import((C.c_ubyte * 64).from_buffer_copy(h), C.byref(peer)), f"bbb_comm_import (rank {q})")
+                self._imported.append(peer.value)
+                ptrs.append(peer.value)
+        self.dist.barrier(group=self.group)
+        return ptrs
+
+    def timeouts(self) -> int:
+        """Exchange waits that gave up because a peer never delivered (results of those steps are invalid)."""
+        return int(self.state[8:12].view(torch.int32).item())
+
+    def close(self):
+        """Unmap the peers' buffers and free the local one (after every rank is done with them)."""
+        lib = L.lib()
+        if self.world > 1 and self._own is not None:
+            torch.cuda.synchronize(self.dev)
+            self.dist.barrier(group=self.group)
+            for p in self._imported:
+                lib.bbb_comm_unimport(C.c_void_p(p))
+            lib.bbb_comm_free(C.c_void_p(self._own))
+            self._imported, self._own = [], None
+
+    # -- one step ----------------------------------------------------------------------------------------------
+    def _step(self, x, base=None):
+        with torch.no_grad():
+            for k, j in enumerate(self.ids):
+                with Fn.stream_base(base), Fn.mc_sample(j, self.seed):
+                    logits, kl = self.net(x)
+                self.logits[k].copy_(logits.reshape(self.B, self.C))
+                if k == 0:
+                    self.kl_one.copy_(torch.as_tensor(kl, dtype=torch.float32, device=self.dev))
+            if not self.ids and self.rank == 0:
+                raise L.EngineError("MCForward: rank 0 must own a sample")
+            o = self.out
+            rc = L.lib().bbb_mc_exchange(
+                Fn._ptr(self.logits), len(self.ids), self.num_ens, self.B, self.C,
+                Fn._ptr(self.kl_one) if self.ids else None, self.flags, Fn._ptr(self.labels),
+                C.c_float(self.train_size), C.c_float(self.beta), self.rank, self.world, self.peers,
+                Fn._ptr(self.state), Fn._ptr(o["log_outputs"]), Fn._ptr(o["kl"]), Fn._ptr(o.get("pred")),
+                Fn._ptr(o.get("epistemic")), Fn._ptr(o.get("aleatoric")), Fn._ptr(o.get("entropy")), Fn._ptr(o.get("head")),
+                Fn._stream(self.dev))
+            L.check(rc, "bbb_mc_exchange")
+        return self.out
+
+    def _capture(self, warmup: int = 2):
+        from .graph import _STRIDE
+        dev = self.dev
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):                 # eager: creates plans / workspaces; every rank runs the same exchanges
+                self._step(self.x, self.base)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        n0 = L.launch_count()
+        with torch.cuda.graph(g):
+            Fn.noise_advance(self.base, _STRIDE)
+            self._step(self.x, self.base)
+        self.kernels_per_step = L.launch_count() - n0
+        self.graph = g
+        self.base.fill_(-_STRIDE)
+
+    def __call__(self, x: Optional[torch.Tensor] = None, labels: Optional[torch.Tensor] = None):
+        if labels is not None:
+            if self.labels is None:
+                raise L.EngineError("MCForward was built without with_labels=True")
+            self.labels.copy_(labels, non_blocking=True)
+        if self.graph is not None:
+            if x is not None:
+                self.x.copy_(x, non_blocking=True)
+            self.graph.replay()
+            self.replays += 1
+            return self.out
+        return self._step(self.x if x is None else x.to(self.dev))
+
+
+def _generic_mc_forward(forward_fn: Callable, x: torch.Tensor, num_ens: int, group=None, want_uncertainty: bool = False):
+    """Backend-agnostic restatement (any device, any torch.distributed backend): the exact (max, sum-exp) partials of
+    logmeanexp per rank and ONE all-gather; returns (log_outputs, kl[, (pred, epistemic, aleatoric, entropy)])."""
+    dist, world, rank = _dist_info(group)
+    ids = local_samples(num_ens, world, rank)
+    parts, shape, dev = None, None, x.device
+    for j in ids:
         logits, kl = forward_fn(x, j)
-        p = torch.softmax(logits.float(), dim=1)
-        part = torch.cat([p.reshape(-1), (p * p).reshape(-1), logits.float().reshape(-1),
-                          torch.as_tensor(kl, dtype=torch.float32, device=logits.device).reshape(1)])
-        acc = part if acc is None else acc + part
-        shape = logits.shape
-    if acc is None:                                   # a rank with no sample (num_ens < world) still joins the collective
-        probe, _ = forward_fn(x, 0)
-        shape = probe.shape
-        acc = torch.zeros(3 * probe.numel() + 1, dtype=torch.float32, device=probe.device)
-    if distributed and world > 1:
-        dist.all_reduce(acc, group=group)             # the ONE collective of the forward path
+        logits = logits.float()
+        shape, dev = logits.shape, logits.device
+        lsm = torch.log_softmax(logits, dim=1)
+        p = lsm.exp()
+        klv = torch.as_tensor(kl, dtype=torch.float32, device=dev).reshape(1)
+        if parts is None:
+            parts = [lsm.clone(), torch.ones_like(lsm), p.clone(), p * p, logits.clone(), klv.clone()]
+        else:
+            m = torch.maximum(parts[0], lsm)
+            parts[1] = parts[1] * (parts[0] - m).exp() + (lsm - m).exp()
+            parts[0] = m
+            parts[2] += p; parts[3] += p * p; parts[4] += logits; parts[5] += klv
+    if world > 1:
+        meta = [tuple(shape) if shape is not None else None]
+        metas = [None] * world
+        dist.all_gather_object(metas, meta[0], group=group)
+        shape = next(s for s in metas if s is not None)
     n = shape[0] * shape[1]
+    if parts is None:                                 # a rank with no sample (num_ens < world) still joins the collective
+        z = torch.zeros(shape, dtype=torch.float32, device=dev)
+        parts = [torch.full(shape, -float("inf"), device=dev), z, z.clone(), z.clone(), z.clone(), torch.zeros(1, device=dev)]
+    vec = torch.cat([t.reshape(-1) for t in parts])
+    if world > 1:
+        allv = [torch.empty_like(vec) for _ in range(world)]
+        dist.all_gather(allv, vec, group=group)       # the ONE collective of the forward path
+    else:
+        allv = [vec]
     S = float(num_ens)
-    p_bar = (acc[:n] / S).view(shape)
-    log_outputs = torch.log(p_bar)                    # == logmeanexp_j log_softmax_j (utils.py:14-22)
-    kl = acc[3 * n] / S                               # main_bayesian.py:51
+    ms = torch.stack([v[:n] for v in allv])
+    as_ = torch.stack([v[n:2 * n] for v in allv])
+    M = ms.max(0).values
+    tot = (as_ * torch.where(as_ > 0, (ms - M).exp(), torch.zeros_like(ms))).sum(0)
+    log_outputs = (M + torch.log(tot / S)).view(shape)         # == logmeanexp_j log_softmax_j (utils.py:14-22), finite
+    kl = sum(v[5 * n] for v in allv) / S                      # main_bayesian.py:51
     if not want_uncertainty:
         return log_outputs, kl
-    p2 = (acc[n:2 * n] / S).view(shape)
-    pred = (acc[2 * n:3 * n] / S).view(shape)
+    p_bar = (sum(v[2 * n:3 * n] for v in allv) / S).view(shape)
+    p2 = (sum(v[3 * n:4 * n] for v in allv) / S).view(shape)
+    pred = (sum(v[4 * n:5 * n] for v in allv) / S).view(shape)
     epistemic = p2 - p_bar * p_bar                    # diag((p-pbar)^T (p-pbar))/T  (uncertainty_estimation.py:89-91)
     aleatoric = p_bar - p2                            # diag(diag(pbar) - p^T p / T)  (:94-95)
     entropy = -(p_bar * torch.log(p_bar.clamp_min(1e-38))).sum(1)      # H[pbar]; no reference (SURVEY D3)
     return log_outputs, kl, (pred, epistemic, aleatoric, entropy)
 
 
-def engine_forward_fn(net) -> Callable:
-    """forward_fn for a net built on the engine: positions the Philox stream at sample j."""
-    from . import functional as Fn
+def mc_forward(net_or_fn, x: torch.Tensor, num_ens: int, group=None, want_uncertainty: bool = False,
+               normalized: bool = False, labels: Optional[torch.Tensor] = None, train_size: float = 1.0,
+               beta: float = 0.0, seed: Optional[int] = None):
+    """(log_outputs [B,C], kl) like main_bayesian.py:46-53 -- plus (pred, epistemic, aleatoric, entropy) like
+    uncertainty_estimation.py:70-96 with ``want_uncertainty`` and the ELBO head [loss, nll, acc, beta*kl] when
+    ``labels`` are given.  ``net_or_fn``: a net built on the engine with CUDA input -> the device path (MCForward,
+    cached on the net per shape/options); any ``forward_fn(x, sample_id) -> (logits, kl)`` -> the generic path."""
+    from .modules import ModuleWrapper
+    if isinstance(net_or_fn, ModuleWrapper) and x.is_cuda:
+        net = net_or_fn
+        key = (tuple(x.shape), int(num_ens), bool(want_uncertainty), bool(normalized), labels is not None,
+               float(train_size), float(beta), seed, id(group))
+        cache = net.__dict__.setdefault("_mc_engines", {})
+        eng = cache.get(key)
+        if eng is None:
+            eng = cache[key] = MCForward(net, x, num_ens, group, want_uncertainty, normalized, labels is not None,
+                                         train_size, beta, seed)
+        out = eng(x, labels)
+        res = [out["log_outputs"], out["kl"]]
+        if want_uncertainty:
+            res.append((out["pred"], out["epistemic"], out["aleatoric"], out["entropy"]))
+        if labels is not None:
+            res.append(out["head"])
+        return tuple(res)
+    return _generic_mc_forward(net_or_fn, x, num_ens, group, want_uncertainty)
 
+
+def engine_forward_fn(net) -> Callable:
+    """forward_fn for a net built on the engine: draws Monte-Carlo sample j (and leaves the training stream untouched)."""
     def fn(x, j):
-        Fn.begin_sample(j)
-        with torch.no_grad():
+        with Fn.mc_sample(j), torch.no_grad():
             return net(x)
     return fn
