@@ -112,17 +112,19 @@ def layer_table(batch, classes=10):
 
 
 def algorithmic(row, variant, act_bytes=4):
+    """F = 2*M*N*K*v; Q = |x|*s + 2*(|W|+|b|)*4 + |y|*s + 4 with s = the run's activation width
+    (4 for the fp32 path, 2 for the bf16 chain -- Appendix C's C3 accounting)."""
     v = 2.0 if variant == "lrt" else 1.0
     flops = row["flops_mean"] * v
     byts = row["x_elems"] * act_bytes + 2 * row["params"] * 4 + row["y_elems"] * act_bytes + 4
     return flops, byts
 
 
-def build_net(variant, classes, device, math):
+def build_net(variant, classes, device, math, net_type="alexnet", inputs=3):
     import pytorch_bayesiancnn_b200 as bbb  # noqa: F401
-    from pytorch_bayesiancnn_b200.models import BBBAlexNet
+    from pytorch_bayesiancnn_b200.models import get_model
     torch.manual_seed(123)
-    net = BBBAlexNet(classes, 3, PRIORS, variant, "softplus")
+    net = get_model(net_type, inputs, classes, PRIORS, variant, "softplus")
     with torch.no_grad():                       # identical params on every rank, drawn on the CPU generator
         g = torch.Generator().manual_seed(123)
         for name, p in net.named_parameters():
@@ -136,9 +138,46 @@ def build_net(variant, classes, device, math):
 # --------------------------------------------------------------------------- #
 # our arm
 # --------------------------------------------------------------------------- #
+def pin_to_gpu_numa_node(local):
+    """Best effort: run this process (and so first-touch its pinned host buffers) on the CPUs of the GPU's NUMA node, so the
+    e2e H2D path does not cross the socket interconnect (round 1 saw 2.96 vs 1.39 M img/s for identical code)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[local]) if vis and vis.split(",")[local].isdigit() else local
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(idx)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return {"numa_node": None}
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus += list(range(int(lo), int(hi or lo) + 1))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "cpus": len(allowed)}
+    except Exception as e:
+        return {"numa_node": None, "note": str(e)[:80]}
+
+
+CONFIGS = {   # BASELINE.json configs restated (SURVEY.md 8d); "headline" = configs[2]'s model/batch, one MC sample per GPU per step
+    "headline": dict(net="alexnet", classes=10, inputs=3, batch=512, variant="lrt", samples=None, uncertainty=False),
+    "C2": dict(net="lenet", classes=10, inputs=3, batch=256, variant="bbb", samples=1, uncertainty=False),
+    "C3": dict(net="alexnet", classes=10, inputs=3, batch=512, variant="lrt", samples=10, uncertainty=False),
+    "C4": dict(net="alexnet", classes=100, inputs=3, batch=1024, variant="lrt", samples=25, uncertainty=False),
+    "C5": dict(net="3conv3fc", classes=10, inputs=1, batch=2048, variant="lrt", samples=100, uncertainty=True),
+}
+
+
 def run_ours(args):
     import pytorch_bayesiancnn_b200 as bbb
-    from pytorch_bayesiancnn_b200 import functional as Fn
+    from pytorch_bayesiancnn_b200 import mc
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -146,25 +185,20 @@ def run_ours(args):
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torch.distributed.run for --gpus > 1")
+    numa = pin_to_gpu_numa_node(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist = None
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
-        # The one collective is a 61 KB all-reduce (latency bound).  Every NCCL channel is a CTA that occupies an SM
-        # while the forward kernels fill all 148 SMs at 1-2 CTAs each: keep the collective to two channels.
-        os.environ.setdefault("NCCL_MAX_NCHANNELS", "2")
-        os.environ.setdefault("NCCL_MIN_NCHANNELS", "1")
-        # NCCL prints its version banner on stdout at communicator creation: keep stdout clean for the one JSON line
+        # NCCL is only the rendezvous here (seed / IPC-handle exchange, barriers, the max-over-ranks of the timings): the
+        # data path of a step is the engine's own NVLink exchange kernel.  Its banner goes to stdout: keep that clean.
         sys.stdout.flush()
         saved_fd = os.dup(1)
         os.dup2(2, 1)
         try:
-            # (the collective itself runs on the process group's internal stream: make that one high priority too)
-            opts = dist.ProcessGroupNCCL.Options()
-            opts.is_high_priority_stream = True
-            dist.init_process_group("nccl", device_id=dev, pg_options=opts)
+            dist.init_process_group("nccl", device_id=dev)
             warm = torch.zeros(1, device=dev)
             dist.all_reduce(warm)
             torch.cuda.synchronize(dev)
@@ -172,141 +206,80 @@ def run_ours(args):
             sys.stdout.flush()
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
-    B, C = args.batch, args.classes
+    cfg = dict(CONFIGS[args.config])
+    if args.config == "headline":
+        cfg.update(batch=args.batch, classes=args.classes, variant=args.variant)
+    B, C = cfg["batch"], cfg["classes"]
+    S_total = cfg["samples"] if cfg["samples"] is not None else world       # headline: one MC sample per GPU per step
+    args.batch, args.classes, args.variant = B, C, cfg["variant"]
     pk = peaks()
 
-    net = build_net(args.variant, C, dev, args.math)
+    net = build_net(cfg["variant"], C, dev, args.math, cfg["net"], cfg["inputs"])
     gx = torch.Generator().manual_seed(0)
+    in_shape = (B, cfg["inputs"], 32, 32)
+    in_bytes = B * cfg["inputs"] * 32 * 32 * 4
     n_inputs = 4                                 # pinned host batches (e2e arm)
-    n_dev_inputs = 24                            # device-resident arm: 24 x 6.3 MB = 151 MB of inputs > 126 MB L2
-    x_host = [torch.randn(B, 3, 32, 32, generator=gx).pin_memory() for _ in range(n_inputs)]
-    x_dev = [torch.randn(B, 3, 32, 32, device=dev) for _ in range(n_dev_inputs)]
-    bbb.manual_seed(2024)
-    # rank r owns MC sample r: its Philox streams start at r << 32 (functional.begin_sample)
-    # one captured forward per resident batch: the graph reads x_dev[k] in place (no staging copy in the step)
-    graphed = bbb.GraphedForward(net, x_dev[0], first_stream=rank << 32, static_inputs=x_dev)
-    # e2e arm: two more captures whose static inputs are the targets of the double-buffered host->device copies
+    n_dev_inputs = max(2, -(-(160 << 20) // in_bytes))   # device-resident arm rotates through > 126 MB (L2) of inputs
+    x_host = [torch.randn(*in_shape, generator=gx).pin_memory() for _ in range(n_inputs)]
+    x_dev = [torch.randn(*in_shape, device=dev) for _ in range(n_dev_inputs)]
+    # The step = the package's public MC step (mc.MCForward): this rank's samples through the engine (fused tcgen05 chain),
+    # then ONE kernel that combines them, exchanges the partials with the other ranks over NVLink and finishes
+    # logmeanexp / KL (/ uncertainty) on the device -- all in one captured CUDA graph per resident input batch.
+    eng = mc.MCForward(net, x_dev[0], S_total, want_uncertainty=cfg["uncertainty"], seed=2024, static_inputs=x_dev)
     staging = [torch.empty_like(x_dev[0]) for _ in range(2)]
-    graphed_e2e = bbb.GraphedForward(net, x_dev[0], first_stream=(rank << 32) + (1 << 30), static_inputs=staging)
-    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    eng_e2e = mc.MCForward(net, x_dev[0], S_total, want_uncertainty=cfg["uncertainty"], seed=2024, static_inputs=staging,
+                           first_replay=1 << 18)
+    S_local = len(eng.ids)
     main = torch.cuda.current_stream(dev)
 
-    # Multi-GPU combine: per-rank reduce of its sample by the engine's MC-combine kernel
-    # (softmax / softmax^2 / logit sums), then ONE NCCL all-reduce of [3*B*C + 1] floats per step.  The collective
-    # runs on its own stream, double buffered, so step i's all-reduce overlaps step i+1's forward.
-    NSLOT = 2
-    # High priority: the all-reduce's two CTAs must not queue behind the forward's kernels, which (chained by PDL)
-    # hand every freed SM straight to the next GEMM; a late collective stalls the two-slot ring below.
-    comm = torch.cuda.Stream(device=dev, priority=-1) if dist is not None else None
-    comb = [torch.zeros(3 * B * C + 1, dtype=torch.float32, device=dev) for _ in range(NSLOT)]
-    outs = [torch.empty(B, C, dtype=torch.float32, device=dev) for _ in range(NSLOT)]
-    lo_scratch = torch.empty(B, C, dtype=torch.float32, device=dev)
-    ev_packed = [torch.cuda.Event() for _ in range(NSLOT)]
-    ev_reduced = [torch.cuda.Event() for _ in range(NSLOT)]
-    extra_launches = [0]
-
-    # The per-step combine is captured too (one graph per slot and stream), so a step costs the host three graph
-    # launches and a few event calls instead of ~10 eager launches (which made N>1 host-bound).
-    pack_graphs, comm_graphs = {}, []
-    if dist is not None:
-        from pytorch_bayesiancnn_b200 import _lib as L_
-
-        def pack(k, out=None):
-            logits, kl = out if out is not None else graphed.outputs[0]
-            rc = L_.lib().bbb_mc_combine(Fn._ptr(logits), 1, B, C, Fn._ptr(lo_scratch), Fn._ptr(comb[k]), Fn._stream(dev))
-            L_.check(rc, "bbb_mc_combine")
-            comb[k][3 * B * C:].copy_(kl.reshape(1))
-
-        def reduce_(k):
-            dist.all_reduce(comb[k])
-            torch.log(comb[k][:B * C] / world, out=outs[k].view(-1))
-
-        for k in range(NSLOT):                       # warm up eagerly (NCCL communicator, allocator), then capture
-            pack(k)
-            with torch.cuda.stream(comm):
-                comm.wait_stream(main)
-                reduce_(k)
-            main.wait_stream(comm)
-        torch.cuda.synchronize(dev)
-        dist.barrier()
-        for gobj in (graphed, graphed_e2e):              # one pack graph per captured forward (its outputs are private)
-            for slot, out in enumerate(gobj.outputs):
-                g1 = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g1):
-                    pack(slot % NSLOT, out)
-                pack_graphs[(id(gobj), slot)] = g1
-        for k in range(NSLOT):
-            g2 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g2, stream=comm):
-                reduce_(k)
-            comm_graphs.append(g2)
-        torch.cuda.synchronize(dev)
-
-    def step(i, gobj, slot):
-        """Step i on static input `slot` of `gobj` (slot parity == i parity, so comm slot k pairs with it)."""
-        logits, kl = gobj(slot=slot)            # forward + KL: one graph launch
-        if dist is None:
-            return logits, kl
-        k = i % NSLOT
-        assert k == slot % NSLOT
-        if i >= NSLOT:
-            main.wait_event(ev_reduced[k])      # slot k is free again
-        pack_graphs[(id(gobj), slot)].replay()  # engine MC-combine kernel + KL into comb[k]
-        extra_launches[0] += 1
-        ev_packed[k].record(main)
-        with torch.cuda.stream(comm):
-            comm.wait_event(ev_packed[k])
-            comm_graphs[k].replay()             # the ONE all-reduce + log
-            ev_reduced[k].record(comm)
-        return outs[k], comb[k][3 * B * C]
-
-    def join():
-        if comm is not None:
-            main.wait_stream(comm)
-
     def sync_all():
-        join()
         torch.cuda.synchronize(dev)
         if dist is not None:
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    # ---- device-resident throughput: K steps back to back, inputs rotate through 151 MB (> L2), one event pair ----
-    for i in range(args.warmup):
-        step(i, graphed, i % n_dev_inputs)
-    sync_all()
+    def window(fn, nsteps):
+        """K steps bracketed by barrier + synchronize on both sides, CUDA events on the launching stream; max over ranks."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        e0.record(main)
+        fn(nsteps)
+        e1.record(main)
+        sync_all()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput: K steps back to back, inputs rotate through > L2 of resident batches ----
+    counter = [0]
+
+    def resident(nsteps):
+        for _ in range(nsteps):
+            eng(slot=counter[0] % n_dev_inputs)
+            counter[0] += 1
+
+    window(resident, args.warmup)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    l0, x0 = graphed.replays, extra_launches[0]
-    assert n_dev_inputs % NSLOT == 0
-    e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     wall0 = time.perf_counter()
-    e_start.record(main)
-    for i in range(args.steps):
-        step(i, graphed, i % n_dev_inputs)      # replays the graph captured on resident batch i % 24
-    join()
-    e_stop.record(main)
-    sync_all()
+    wins = [window(resident, args.steps) for _ in range(args.windows)]
     wall = time.perf_counter() - wall0
-    launches = (graphed.replays - l0) * graphed.kernels_per_replay + (extra_launches[0] - x0)   # engine kernels in the timed steps
-    t_ms = torch.tensor([e_start.elapsed_time(e_stop)], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(t_ms.item())
-    value = B * world * args.steps / (total_ms * 1e-3)
+    total_ms = statistics.median(wins)
+    images_per_step = B * S_total                # image-samples of the whole job per step (SURVEY 8d: B*S/t)
+    value = images_per_step * args.steps / (total_ms * 1e-3)
+    launches = eng.kernels_per_step * args.steps
 
-    # ---- end to end through the public API: pinned host input -> H2D -> forward -> D2H ----
+    # ---- end to end through the public API: pinned host input -> H2D -> MC step -> D2H of the result ----
     out_host = torch.empty(B, C, dtype=torch.float32).pin_memory()
     kl_host = torch.empty(1, dtype=torch.float32).pin_memory()
     copy_stream = torch.cuda.Stream(device=dev)
     ready = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
-    def e2e_run(nsteps):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        sync_all()
-        e0.record(main)
-        copy_stream.wait_event(e0)
+
+    def e2e_steps(nsteps):
+        copy_stream.wait_stream(main)
         with torch.cuda.stream(copy_stream):
             staging[0].copy_(x_host[0], non_blocking=True)
             ready[0].record(copy_stream)
@@ -319,123 +292,130 @@ def run_ours(args):
                     staging[s ^ 1].copy_(x_host[(i + 1) % n_inputs], non_blocking=True)
                     ready[s ^ 1].record(copy_stream)
             main.wait_event(ready[s])
-            lo, kl = step(i, graphed_e2e, s)
+            out = eng_e2e(slot=s)
             consumed[s].record(main)
-            if comm is not None:
-                main.wait_event(ev_reduced[i % NSLOT])   # the combined result comes from the collective's stream
-            out_host.copy_(lo, non_blocking=True)
-            kl_host.copy_(kl.reshape(1), non_blocking=True)
-        join()
-        e1.record(main)
-        sync_all()
-        return e0.elapsed_time(e1)
+            out_host.copy_(out["log_outputs"], non_blocking=True)
+            kl_host.copy_(out["kl"].reshape(1), non_blocking=True)
 
-    e2e_run(max(3, args.warmup))
-    e_ms = torch.tensor([e2e_run(args.steps)], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
-    e2e_value = B * world * args.steps / (float(e_ms.item()) * 1e-3)
+    window(e2e_steps, max(3, args.warmup))
+    e2e_wins = [window(e2e_steps, args.steps) for _ in range(max(5, args.windows // 3))]
+    e2e_ms = statistics.median(e2e_wins)
+    e2e_value = images_per_step * args.steps / (e2e_ms * 1e-3)
     clocks = sampler.stop() if rank == 0 else None
+    timeouts = eng.timeouts() + eng_e2e.timeouts()
 
-    # ---- optional extra figure: S independent forwards in flight on S streams (not the headline) ----
-    streams_fig = None
-    if args.streams > 1 and dist is None:
-        S = args.streams
-        strs = [torch.cuda.Stream(device=dev) for _ in range(S)]
-        gs = [bbb.GraphedForward(net, x_dev[0], first_stream=(rank << 32) + ((s + 1) << 26),
-                                 static_inputs=x_dev[s::S], ws_slot=s + 1) for s in range(S)]
-
-        def streams_run(n):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize(dev)
-            e0.record(main)
-            for st in strs:
-                st.wait_event(e0)
-            for i in range(n):
-                s = i % S
-                with torch.cuda.stream(strs[s]):
-                    gs[s](slot=(i // S) % len(gs[s].inputs))
-            for st in strs:
-                main.wait_stream(st)
-            e1.record(main)
-            torch.cuda.synchronize(dev)
-            return e0.elapsed_time(e1)
-
-        streams_run(max(args.warmup, 3) * S)
-        t_s = streams_run(args.steps)
-        streams_fig = {"streams": S, "ms_per_step": t_s / args.steps, "value": B * args.steps / (t_s * 1e-3),
-                       "unit": "images/s",
-                       "note": "separate figure, not the headline: independent forwards of different resident batches "
-                               "overlap on S streams (per-stream layer workspaces and noise bases)"}
-
-    # ---- per-layer kernel timing + roofline of the dominant kernel (rank 0) ----
+    # ---- per-layer kernel timing + roofline of the dominant kernel (rank 0, AlexNet only) ----
     per_layer, roof = [], None
-    if rank == 0:
+    if rank == 0 and cfg["net"] == "alexnet":
+        flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
         per_layer, roof = layer_rooflines(net, x_dev[0], args, pk, flush)
+        del flush
 
     mc_batched = None
-    if rank == 0 and world == 1 and args.variant == "lrt" and args.mc_batch > 1:
-        # S Monte-Carlo samples folded into ONE launch: for LRT the samples differ only in the per-activation noise, so
-        # S samples of a batch == one batch of S*B rows (what uncertainty_estimation.py:38-41 does); KL computed once.
+    if rank == 0 and world == 1 and args.config == "headline" and cfg["variant"] == "lrt" and args.mc_batch > 1:
+        # configs[2] literally: S = 10 MC samples of the batch.  For LRT the samples differ only in the per-activation
+        # noise, so S samples == one launch over S*B rows (what uncertainty_estimation.py:38-41 does); KL computed once.
         S = args.mc_batch
         xb = x_dev[0].repeat(S, 1, 1, 1)
         gb = bbb.GraphedForward(net, xb, first_stream=1 << 40)
         for _ in range(3):
             gb()
         torch.cuda.synchronize(dev)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 20
-        e0.record()
-        for _ in range(reps):
-            gb()
-        e1.record()
-        torch.cuda.synchronize(dev)
-        ms = e0.elapsed_time(e1) / reps
+        ts = []
+        for _ in range(9):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                gb()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ts.append(e0.elapsed_time(e1) / 10)
+        ms = statistics.median(ts)
+        fl = sum(algorithmic(r, "lrt", 2)[0] for r in layer_table(S * B, C))
+        t_roof = sum(max(algorithmic(r, "lrt", 2)[0] / (pk["tf_sustained"] * 1e12), algorithmic(r, "lrt", 2)[1] / (pk["hbm_gbs"] * 1e9))
+                     for r in layer_table(S * B, C))
         mc_batched = {"mc_samples": S, "rows_per_launch": S * B, "ms_per_launch": ms,
-                      "value": S * B / (ms * 1e-3), "unit": "sample-images/s",
-                      "note": "separate figure, not the headline: S samples of the same 512 images per launch (LRT only)"}
+                      "value": S * B / (ms * 1e-3), "unit": "sample-images/s", "tflops": fl / (ms * 1e-3) / 1e12,
+                      "roofline_frac_of_sustained_peak": t_roof / (ms * 1e-3),
+                      "note": "configs[2] as written: 10 MC samples of the 512 images in ONE launch (LRT: samples fold into the batch)"}
         del gb, xb
 
-    cpu = None
+    cpu = incumbent = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference(args, seconds=args.cpu_seconds)
+        if cfg["net"] == "alexnet":
+            incumbent = gpu_eager_incumbent(args, dev)
 
     if rank == 0:
+        dt = "f32" if args.math == "fp32" else "bf16 operands, f32 accumulate"
         out = {
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if args.math == "fp32" else "bf16 operands, f32 accumulate",
+            "scaling": "weak" if cfg["samples"] is None else "strong", "vs_baseline": None, "dtype": dt,
             "data": "synthetic (randn inputs, random-init params N(0,0.1)/rho N(-5,0.1))",
-            "config": {"workload": f"BBBAlexNet-{C} CIFAR-10 shape 3x32x32, batch {B}, {args.variant} layers, "
-                                   f"softplus, 1 MC sample per GPU per step (MC samples sharded over GPUs)",
-                       "named_config": ("BASELINE.json configs[2] (BBBAlexNet CIFAR-10 batch 512 bf16, 10 MC samples, 1xB200, "
-                                        "BBB_LRT): a step is ONE MC sample of the batch and the metric counts image-samples "
-                                        "(B*S/t, SURVEY 8d), so the 10-sample loop has this same throughput; the single-launch "
-                                        "S=10 figure is reported separately under mc_batched")
-                       if (args.variant, args.math, B, C) == ("lrt", "bf16", 512, 10) else None,
-                       "batch": B, "variant": args.variant, "math": args.math, "mc_samples_total": world,
-                       "parallelism": f"mc{world}", "l2": "no flush: inputs rotate through 24 resident batches = 151 MB > 126 MB L2",
-                       "launch": "CUDA graph replay of the full forward (noise advance, per-layer prep + GEMM kernels, KL sum); one captured graph per resident input batch, read in place"},
-            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * 3 * 32 * 32 * 4,
-                    "d2h_bytes_per_step": B * C * 4 + 4},
+            "config": {"workload": f"BBB{cfg['net']}-{C} {cfg['inputs']}x32x32, batch {B}, {cfg['variant']} layers, softplus, "
+                                   f"{S_total} MC sample(s) per step sharded over {world} GPU(s) ({S_local} on rank 0); step = "
+                                   f"forward+KL of the local samples + the MC combine/exchange kernel",
+                       "named_config": args.config if args.config != "headline" else
+                                       ("BASELINE.json configs[2] model/batch (BBBAlexNet CIFAR-10 batch 512 bf16, BBB_LRT): a step is ONE MC "
+                                        "sample of the batch per GPU and the metric counts image-samples (B*S/t, SURVEY 8d); the literal "
+                                        "single-launch S=10 figure is under mc_batched"),
+                       "batch": B, "variant": cfg["variant"], "math": args.math, "mc_samples_total": S_total,
+                       "parallelism": f"mc{world}",
+                       "l2": f"no flush: inputs rotate through {n_dev_inputs} resident batches = {n_dev_inputs * in_bytes >> 20} MB > 126 MB L2",
+                       "launch": "one CUDA graph replay per step (noise advance, per-layer prep + GEMM kernels, KL sum, MC exchange "
+                                 "kernel over NVLink peer memory); one captured graph per resident input batch, read in place",
+                       "timing": f"median of {args.windows} windows of {args.steps} steps, each bracketed by barrier+synchronize, "
+                                 f"CUDA events, max over ranks per window"},
+            "windows_ms": {"min": min(wins), "median": total_ms, "max": max(wins), "n": len(wins)},
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": in_bytes,
+                    "d2h_bytes_per_step": B * C * 4 + 4, "windows_ms": {"min": min(e2e_wins), "median": e2e_ms, "max": max(e2e_wins)},
+                    "host_numa": numa},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof,
             "per_layer": per_layer,
-            "streams": streams_fig,
             "cpu_baseline": cpu,
+            "gpu_eager_incumbent": incumbent,
             "mc_batched": mc_batched,
+            "exchange_timeouts": timeouts,
             "wall_s_timed_loop": wall,
         }
         print(json.dumps(out), flush=True)
+    sync_all()
+    eng.close(); eng_e2e.close()
     if dist is not None:
-        # leave without tearing NCCL down under live CUDA graphs (observed to hang at exit); every rank has
-        # synchronised and rank 0 has printed
-        sys.stdout.flush(); sys.stderr.flush()
-        torch.cuda.synchronize(dev)
-        dist.barrier()
-        os._exit(0)
+        dist.destroy_process_group()
+
+
+def gpu_eager_incumbent(args, dev, reps=12):
+    """SURVEY 8d's same-box incumbent: the reference's op sequence in stock PyTorch eager ON THE B200 (the oracle port's
+    aten calls with CUDA tensors -- cuDNN conv (TF32 by default) + elementwise launches), including what the
+    reference does every forward: eps drawn on the CPU generator and copied host->device (BBB/BBBConv.py:63,68)."""
+    try:
+        from oracle import bbb_oracle as O               # baseline leg only
+        params = [{k: v.to(dev) for k, v in p.items()} for p in O.init_params("alexnet", args.classes, 3, PRIORS, seed=123)]
+        x = torch.randn(args.batch, 3, 32, 32, generator=torch.Generator().manual_seed(0)).to(dev)
+        shapes = O.eps_shapes("alexnet", args.classes, 3, args.variant, args.batch)
+
+        def one():
+            with torch.no_grad():
+                eps = [torch.empty(s).normal_(0, 1).to(dev) for s in shapes]
+                logits, kl = O.net_forward("alexnet", params, x, eps, args.variant, "softplus", 0.0, 0.1, args.classes)
+                return float(kl)                          # main_bayesian.py:52 (kl.item(): the per-step host sync)
+        for _ in range(3):
+            one()
+        ts = []
+        for _ in range(reps):
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter(); one(); torch.cuda.synchronize(dev)
+            ts.append(time.perf_counter() - t0)
+        med = statistics.median(ts)
+        return {"value": args.batch / med, "unit": "images/s", "ms_per_step": med * 1e3, "min_ms": min(ts) * 1e3,
+                "what": "oracle port's aten ops on the same B200, eager, incl. per-forward CPU eps draw + H2D copy and the "
+                        "kl.item() sync (reference semantics); wall clock around synchronize"}
+    except Exception as e:
+        return {"value": None, "note": f"failed: {e}"[:200]}
 
 
 def layer_rooflines(net, x, args, pk, flush, reps=20):
@@ -446,6 +426,7 @@ def layer_rooflines(net, x, args, pk, flush, reps=20):
     import pytorch_bayesiancnn_b200 as bbb
     from pytorch_bayesiancnn_b200 import fused
     rows = layer_table(args.batch, args.classes)
+    act_b = 4 if args.math == "fp32" else 2              # activation width of this run (C3 uses s = 2)
     steps = fused.plan(list(net.children()), tuple(x.shape)) if getattr(net, "fuse", True) else None
     calls = []
     with torch.no_grad():
@@ -488,7 +469,7 @@ def layer_rooflines(net, x, args, pk, flush, reps=20):
         # the two kernels of a fused-chain layer timed alone: parameter-only prep, and the GEMM kernel
         ms_prep = timed(lambda: call(ph=L.FUSED_PREP_ONLY)) if steps is not None else None
         ms_gemm = timed(lambda: call(ph=L.FUSED_SKIP_PREP)) if steps is not None else None
-        fl, by = algorithmic(row, args.variant)
+        fl, by = algorithmic(row, args.variant, act_b)
         t_tc = fl / (pk["tf_burst"] * 1e12)
         t_hbm = by / (pk["hbm_gbs"] * 1e9)
         bound = "tensor" if t_tc >= t_hbm else "hbm"
@@ -515,14 +496,14 @@ def layer_rooflines(net, x, args, pk, flush, reps=20):
                 "unit": "GB/s", "frac": top["mbytes"] / 1e3 / t_k / pk["hbm_gbs"], "traffic": None,
                 "peak_source": pk["source"],
                 "kernel_us": t_k * 1e6, "layer_us_prep_plus_gemm": top["ms"] * 1e3, "layer_frac": top["frac"]}
-    tp = os.path.join(ROOT, "profiles", "r1_ncu_full_gemm_final_traffic.json")      # dram__bytes_read+write of that kernel, one ncu --set full capture
+    tp = os.path.join(ROOT, "profiles", "r2_ncu_full_traffic.json")      # dram__bytes_read+write of that kernel, one ncu --set full capture
     if os.path.exists(tp):
         tj = json.load(open(tp))
         if tj.get("variant") == args.variant and tj.get("batch") == args.batch and top["name"] in tj["layers"]:
             roof["traffic"] = tj["layers"][top["name"]]["dram_bytes"]
             roof["traffic_source"] = tj["source"]
-    t_roof = sum(max(algorithmic(r, args.variant)[0] / (pk["tf_burst"] * 1e12),
-                     algorithmic(r, args.variant)[1] / (pk["hbm_gbs"] * 1e9)) for r in rows)
+    t_roof = sum(max(algorithmic(r, args.variant, act_b)[0] / (pk["tf_burst"] * 1e12),
+                     algorithmic(r, args.variant, act_b)[1] / (pk["hbm_gbs"] * 1e9)) for r in rows)
     roof["net_t_roof_us"] = t_roof * 1e6
     roof["net_layer_kernels_us"] = sum(r["ms"] for r in out) * 1e3
     return out, roof
@@ -550,15 +531,15 @@ def pick_threads(one):
 
 def cpu_step_fn(args):
     from oracle import bbb_oracle as O               # bench's cpu_baseline leg may use the oracle
-    params = O.init_params("alexnet", args.classes, 3, PRIORS, seed=123)
-    x = torch.randn(args.batch, 3, 32, 32, generator=torch.Generator().manual_seed(0))
-    shapes = O.eps_shapes("alexnet", args.classes, 3, args.variant, args.batch)
+    params = O.init_params(args.net_type, args.classes, args.inputs, PRIORS, seed=123)
+    x = torch.randn(args.batch, args.inputs, 32, 32, generator=torch.Generator().manual_seed(0))
+    shapes = O.eps_shapes(args.net_type, args.classes, args.inputs, args.variant, args.batch)
 
     def one():
         with torch.no_grad():
             # the reference draws eps on the CPU generator inside every forward (BBB/BBBConv.py:63)
             eps = [torch.empty(s).normal_(0, 1) for s in shapes]
-            logits, kl = O.net_forward("alexnet", params, x, eps, args.variant, "softplus", 0.0, 0.1, args.classes)
+            logits, kl = O.net_forward(args.net_type, params, x, eps, args.variant, "softplus", 0.0, 0.1, args.classes)
             return float(kl) + float(logits[0, 0])
     return one
 
@@ -567,7 +548,7 @@ def cpu_reference(args, seconds=10.0):
     """cpu_baseline leg: the reference arm in a fresh process (no CUDA context, no
     clock sampler competing for cores), bounded to ~`seconds` of CPU work."""
     cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "12", "--warmup", "3",
-           "--variant", args.variant, "--batch", str(args.batch), "--classes", str(args.classes)]
+           "--variant", args.variant, "--batch", str(args.batch), "--classes", str(args.classes), "--config", args.config]
     try:
         out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT).stdout.strip().splitlines()
         d = json.loads(out[-1])
@@ -603,9 +584,9 @@ def run_reference(args):
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus,
            "steps": steps, "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": f"BBBAlexNet-{args.classes} CIFAR-10 shape 3x32x32, batch {args.batch}, "
+           "config": {"workload": f"BBB{args.net_type}-{args.classes} {args.inputs}x32x32, batch {args.batch}, "
                                   f"{args.variant} layers, softplus, 1 MC sample per step", "batch": args.batch,
-                      "variant": args.variant},
+                      "variant": args.variant, "named_config": args.config},
            "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port",
                             "sample": f"{steps} forwards of the full batch-{args.batch} workload (median "
                                       f"{statistics.median(ts) * 1e3:.1f} ms, min {min(ts) * 1e3:.1f} ms); torch-CPU "
@@ -630,10 +611,15 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mc-batch", type=int, default=10, help="also report S MC samples folded into one launch (LRT; 0 = skip)")
-    ap.add_argument("--streams", type=int, default=1,
-                    help="extra figure (single GPU): that many forward graphs in flight on separate streams; 1 = off")
+    ap.add_argument("--windows", type=int, default=25, help="timed windows of --steps steps; the median window is reported")
+    ap.add_argument("--config", default="headline", choices=list(CONFIGS),
+                    help="headline (default: BBBAlexNet-10 B=512, one MC sample per GPU per step) or one of BASELINE.json's configs restated")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    cfg = CONFIGS[args.config]
+    if args.config != "headline":
+        args.batch, args.classes, args.variant = cfg["batch"], cfg["classes"], cfg["variant"]
+    args.net_type, args.inputs = cfg["net"], cfg["inputs"]
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -132,9 +132,13 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw32(uint32_t saddr, uint32_t
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (6ull << 61);
 }
 __device__ __forceinline__ uint32_t sw32(uint32_t addr) { return addr ^ (((addr >> 7) & 1u) << 4); }
-__device__ __forceinline__ void sts128(uint32_t saddr, uint4 v) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                   "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])) : "memory");
 }
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 template <int VARIANT>
 __global__ void __launch_bounds__(S4_THREADS, 1)
 conv_s4_kernel(const S4Args p) {
@@ -166,7 +170,7 @@ conv_s4_kernel(const S4Args p) {
         mbar_init(smem_u32(&ctl->img_ready), 256);
         fence_barrier_init();
     }
-    const uint32_t tmem_cols = two ? 256u : 128u;
+    const uint32_t tmem_cols = (two && !p.eps_a) ? 512u : (two ? 256u : 128u);      // accumulators (+ the LRT noise tile)
     if (warp == 8) tmem_alloc(smem_u32(&ctl->tmem_base), tmem_cols);
     pdl_wait();                                                  // everything below reads / writes tensors other kernels touch
     if (threadIdx.x < 64) {
@@ -188,36 +192,48 @@ conv_s4_kernel(const S4Args p) {
         const int zc = chunks_row - (data_c1 - data_c0);                     // halo chunks per row
         const int n_zero = S4_IMGS * p.rows * zc;
         const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+        auto sptr = [&](uint32_t saddr) { return reinterpret_cast<uint4*>(sm + (sw32(saddr) - base)); };   // swizzled 16-byte slot
         for (int it = t; it < n_zero; it += 256) {
             const int rowi = it / zc, k = it - rowi * zc;
             const int chunk = k < data_c0 ? k : data_c1 + (k - data_c0);
             const uint32_t off = (uint32_t)rowi * rowb + (uint32_t)chunk * 16u;
-            sts128(sw32(imgx + off), z4);
-            if (two) sts128(sw32(imgx2 + off), z4);
+            *sptr(imgx + off) = z4;
+            if (two) *sptr(imgx2 + off) = z4;
         }
         const size_t chw = (size_t)g.Cin * g.HW;
-#pragma unroll 2
-        for (int it = t; it < n_data; it += 256) {
-            const int gq = it % groups, rowi = it / groups;                  // rowi = image * rows + staged row
-            const int i = rowi / p.rows, lr = rowi - i * p.rows;
-            const int ih = row0 + lr, b = img0 + i;
-            float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0, c2 = c0, c3 = c0;
-            if (b < g.B && (unsigned)ih < (unsigned)g.H) {
-                const float* src = p.x + (size_t)b * chw + (size_t)ih * g.W + gq * 4;
-                c0 = __ldg(reinterpret_cast<const float4*>(src));
-                if (g.Cin > 1) c1 = __ldg(reinterpret_cast<const float4*>(src + g.HW));
-                if (g.Cin > 2) c2 = __ldg(reinterpret_cast<const float4*>(src + 2 * g.HW));
-                if (g.Cin > 3) c3 = __ldg(reinterpret_cast<const float4*>(src + 3 * g.HW));
+        constexpr int SB = 4;                                               // items in flight per thread: 12 independent 16-byte loads
+#pragma unroll 1
+        for (int it0 = t; it0 < n_data; it0 += 256 * SB) {
+            float4 c[SB][4];
+            uint32_t off[SB];
+#pragma unroll
+            for (int u = 0; u < SB; ++u) {
+                const int it = it0 + 256 * u;
+                const int gq = it % groups, rowi = it / groups;              // rowi = image * rows + staged row
+                const int i = rowi / p.rows, lr = rowi - i * p.rows;
+                const int ih = row0 + lr, b = img0 + i;
+                c[u][0] = c[u][1] = c[u][2] = c[u][3] = make_float4(0.f, 0.f, 0.f, 0.f);
+                off[u] = it < n_data ? (uint32_t)rowi * rowb + (uint32_t)(p.lpad + gq * 4) * 8u : 0xffffffffu;   // 16-byte aligned: lpad even
+                if (it < n_data && b < g.B && (unsigned)ih < (unsigned)g.H) {
+                    const float* src = p.x + (size_t)b * chw + (size_t)ih * g.W + gq * 4;
+                    c[u][0] = __ldg(reinterpret_cast<const float4*>(src));
+                    if (g.Cin > 1) c[u][1] = __ldg(reinterpret_cast<const float4*>(src + g.HW));
+                    if (g.Cin > 2) c[u][2] = __ldg(reinterpret_cast<const float4*>(src + 2 * g.HW));
+                    if (g.Cin > 3) c[u][3] = __ldg(reinterpret_cast<const float4*>(src + 3 * g.HW));
+                }
             }
-            const uint32_t off = (uint32_t)rowi * rowb + (uint32_t)(p.lpad + gq * 4) * 8u;   // 16-byte aligned: lpad even
-            const uint4 a = make_uint4(pack_bf16(c0.x, c1.x), pack_bf16(c2.x, c3.x), pack_bf16(c0.y, c1.y), pack_bf16(c2.y, c3.y));
-            const uint4 bq = make_uint4(pack_bf16(c0.z, c1.z), pack_bf16(c2.z, c3.z), pack_bf16(c0.w, c1.w), pack_bf16(c2.w, c3.w));
-            sts128(sw32(imgx + off), a);
-            sts128(sw32(imgx + off + 16u), bq);
-            if (two) {
-                // squares of the bf16-rounded values (what the mean path multiplies), one rounding
-                sts128(sw32(imgx2 + off), make_uint4(bf16x2_sq(a.x), bf16x2_sq(a.y), bf16x2_sq(a.z), bf16x2_sq(a.w)));
-                sts128(sw32(imgx2 + off + 16u), make_uint4(bf16x2_sq(bq.x), bf16x2_sq(bq.y), bf16x2_sq(bq.z), bf16x2_sq(bq.w)));
+#pragma unroll
+            for (int u = 0; u < SB; ++u) {
+                if (off[u] == 0xffffffffu) continue;
+                const uint4 a = make_uint4(pack_bf16(c[u][0].x, c[u][1].x), pack_bf16(c[u][2].x, c[u][3].x), pack_bf16(c[u][0].y, c[u][1].y), pack_bf16(c[u][2].y, c[u][3].y));
+                const uint4 bq = make_uint4(pack_bf16(c[u][0].z, c[u][1].z), pack_bf16(c[u][2].z, c[u][3].z), pack_bf16(c[u][0].w, c[u][1].w), pack_bf16(c[u][2].w, c[u][3].w));
+                *sptr(imgx + off[u]) = a;
+                *sptr(imgx + off[u] + 16u) = bq;
+                if (two) {
+                    // squares of the bf16-rounded values (what the mean path multiplies), one rounding
+                    *sptr(imgx2 + off[u]) = make_uint4(bf16x2_sq(a.x), bf16x2_sq(a.y), bf16x2_sq(a.z), bf16x2_sq(a.w));
+                    *sptr(imgx2 + off[u] + 16u) = make_uint4(bf16x2_sq(bq.x), bf16x2_sq(bq.y), bf16x2_sq(bq.z), bf16x2_sq(bq.w));
+                }
             }
         }
         fence_proxy_async();                                                // generic-proxy stores -> visible to the tensor core
@@ -229,18 +245,28 @@ conv_s4_kernel(const S4Args p) {
         const int i = m >> 3, ow = m & 7, b = img0 + i;
         const bool bvalid = b < g.B;
         const bool philox = two && !p.eps_a;
-        float ez[2][32];
-        if (philox && bvalid) {
+        // Noise goes to TENSOR MEMORY (columns behind the accumulators, this thread's lane): 64 values per thread would
+        // otherwise pin 64 registers and force the epilogue to be fully unrolled (register arrays cannot be indexed by a
+        // loop counter) -- straight-line code executed once per CTA, which is what the cold instruction cache punishes.
+        const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(half * 32);
+        const uint32_t noise_col = 256u;
+        if (philox) {
             const NoiseKey nkey = effective_key(p.key, p.stream_base);
+#pragma unroll 1
+            for (int it = 0; it < 8; ++it) {
+                const int ohl = it >> 2, k8 = it & 3;
+                float z8[8];
+                if (bvalid) {
+                    const uint64_t o0 = ((uint64_t)b * g.OHW + (uint64_t)((2 * ohp + ohl) * g.OW + ow)) * g.N + half * 32 + k8 * 8;
+                    const float4 za = normal4(o0 >> 2, nkey), zb = normal4((o0 >> 2) + 1, nkey);   // N == 64: four channels per Philox call
+                    z8[0] = za.x; z8[1] = za.y; z8[2] = za.z; z8[3] = za.w; z8[4] = zb.x; z8[5] = zb.y; z8[6] = zb.z; z8[7] = zb.w;
+                } else {
 #pragma unroll
-            for (int ohl = 0; ohl < 2; ++ohl) {
-                const uint64_t o0 = ((uint64_t)b * g.OHW + (uint64_t)((2 * ohp + ohl) * g.OW + ow)) * g.N + half * 32;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const float4 z = normal4((o0 >> 2) + k, nkey);          // N == 64: four channels per Philox call
-                    ez[ohl][4 * k] = z.x; ez[ohl][4 * k + 1] = z.y; ez[ohl][4 * k + 2] = z.z; ez[ohl][4 * k + 3] = z.w;
+                    for (int j = 0; j < 8; ++j) z8[j] = 0.0f;
                 }
+                tmem_st8(lane_base + noise_col + (uint32_t)(ohl * 64 + k8 * 8), z8);
             }
+            tmem_st_wait();
         }
         if (tr && threadIdx.x == 0) tr[3] = clock64();
 
@@ -248,53 +274,52 @@ conv_s4_kernel(const S4Args p) {
         mbar_wait(smem_u32(&ctl->accum), 0u);
         tc_fence_after();
         if (tr && threadIdx.x == 0) tr[5] = clock64();
-        const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(half * 32);
         // the other column of the 2x2 window lives in the neighbouring lane; after the shuffle both lanes hold the pooled
         // value: the even lane stores y, the odd lane y^2 (act is monotone: act(max) == max(act))
         const bool odd = ow & 1;
         const int pp = ohp * (g.OW >> 1) + (ow >> 1);
         const int kb_total = p.out_pitch >> 6, planes_out = p.y_sq ? 2 : 1;
-#pragma unroll
-        for (int c16 = 0; c16 < 2; ++c16) {                                 // 16 of this thread's 32 columns at a time
-            float best[16];
+#pragma unroll 1
+        for (int c8 = 0; c8 < 4; ++c8) {                                    // 8 of this thread's 32 columns per iteration
+            const int n0 = half * 32 + c8 * 8;
+            float best[8];
 #pragma unroll
             for (int ohl = 0; ohl < 2; ++ohl) {
-                float am[16];
-                tmem_ld16(lane_base + (uint32_t)(ohl * p.planes * 64 + c16 * 16), am);
+                float am[8];
+                tmem_ld8(lane_base + (uint32_t)(ohl * p.planes * 64 + c8 * 8), am);
                 if (two) {
-                    float av[16];
-                    tmem_ld16(lane_base + (uint32_t)(ohl * 128 + 64 + c16 * 16), av);
+                    float av[8], e8[8];
+                    tmem_ld8(lane_base + (uint32_t)(ohl * 128 + 64 + c8 * 8), av);
+                    if (philox) tmem_ld8(lane_base + noise_col + (uint32_t)(ohl * 64 + c8 * 8), e8);
+                    else {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int n = half * 32 + c16 * 16 + j;
-                        float e_;
-                        if (philox) e_ = ez[ohl][c16 * 16 + j];
-                        else e_ = bvalid ? __ldg(p.eps_a + ((size_t)b * g.N + n) * g.OHW + (2 * ohp + ohl) * g.OW + ow) : 0.0f;
-                        const float var = 1e-16f + (av[j] + ctl->bvar[n]);
-                        am[j] = am[j] + ctl->bias[n] + fast_sqrt(var) * e_;
+                        for (int j = 0; j < 8; ++j)
+                            e8[j] = bvalid ? __ldg(p.eps_a + ((size_t)b * g.N + n0 + j) * g.OHW + (2 * ohp + ohl) * g.OW + ow) : 0.0f;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float var = 1e-16f + (av[j] + ctl->bvar[n0 + j]);
+                        am[j] = am[j] + ctl->bias[n0 + j] + fast_sqrt(var) * e8[j];
                     }
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) am[j] += ctl->bias[half * 32 + c16 * 16 + j];
+                    for (int j = 0; j < 8; ++j) am[j] += ctl->bias[n0 + j];
                 }
 #pragma unroll
-                for (int j = 0; j < 16; ++j) best[j] = ohl ? fmaxf(best[j], am[j]) : am[j];
+                for (int j = 0; j < 8; ++j) best[j] = ohl ? fmaxf(best[j], am[j]) : am[j];
             }
+            float v[8];
 #pragma unroll
-            for (int c8 = 0; c8 < 2; ++c8) {
-                float v[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float q = best[c8 * 8 + j];
-                    q = fmaxf(q, __shfl_xor_sync(0xffffffffu, q, 1));
-                    q = fast_act(q, p.act);
-                    v[j] = odd ? q * q : q;
-                }
-                if (bvalid && (!odd || p.y_sq)) {
-                    const size_t off = tiled_chunk_offset(b, pp * g.N + half * 32 + c16 * 16 + c8 * 8, kb_total, planes_out);
-                    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(odd ? p.y_sq : p.y) + off;
-                    *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-                }
+            for (int j = 0; j < 8; ++j) {
+                float q = best[j];
+                q = fmaxf(q, __shfl_xor_sync(0xffffffffu, q, 1));
+                q = fast_act(q, p.act);
+                v[j] = odd ? q * q : q;
+            }
+            if (bvalid && (!odd || p.y_sq)) {
+                const size_t off = tiled_chunk_offset(b, pp * g.N + n0, kb_total, planes_out);
+                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(odd ? p.y_sq : p.y) + off;
+                *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
             }
         }
         if (tr && threadIdx.x == 0) tr[6] = clock64();
@@ -310,6 +335,7 @@ conv_s4_kernel(const S4Args p) {
             __syncwarp();                                                   // converged whole-warp wait (single-lane waits wake late)
             mbar_wait(smem_u32(&ctl->full[s]), (uint32_t)(r / S4_STAGES) & 1u);
             tc_fence_after();
+            if (tr && lane == 0) tr[8 + r] = clock64();
             if (lane == 0) {
                 const uint32_t st = ring + (uint32_t)s * stage_bytes;
 #pragma unroll
@@ -327,6 +353,7 @@ conv_s4_kernel(const S4Args p) {
                 }
                 umma_commit(smem_u32(&ctl->empty[s]));
                 if (r == g.KH - 1) umma_commit(smem_u32(&ctl->accum));
+                if (tr) tr[24 + r] = clock64();
             }
             __syncwarp();
         }

@@ -108,7 +108,7 @@ mc_exchange_kernel(const McxArgs p) {
                 if (p.normalized) { pr = softplus_f(l) / norm_s[warp][s]; lp = logf(pr); }
                 else { lp = l - norm_s[warp][s]; pr = expf(lp); }            // log_softmax (main_bayesian.py:49)
                 if (lp > mx) { acc = acc * expf(mx - lp) + 1.0f; mx = lp; }  // online logsumexp over the samples
-                else acc += expf(lp - mx);
+                else if (lp > -INFINITY) acc += expf(lp - mx);               // lp == -inf: a probability of exactly 0 adds nothing
                 sp += pr; sp2 += pr * pr; sl += l;
             }
             const size_t e = (size_t)b * C + c;

@@ -63,7 +63,11 @@ class MCForward:
 
     def __init__(self, net, example_x: torch.Tensor, num_ens: int, group=None, want_uncertainty: bool = False,
                  normalized: bool = False, with_labels: bool = False, train_size: float = 1.0, beta: float = 0.0,
-                 seed: Optional[int] = None, graph: bool = True, num_classes: Optional[int] = None):
+                 seed: Optional[int] = None, graph: bool = True, num_classes: Optional[int] = None,
+                 static_inputs=None, first_replay: int = 0):
+        """``static_inputs``: device tensors the caller fills in place (e.g. targets of its host->device copies, or a
+        rotation of resident batches); one graph is captured per tensor and ``self(slot=k)`` runs the step on
+        ``static_inputs[k]`` with no staging copy.  ``first_replay``: index of the first replay's noise block."""
         Fn._require_cuda(example_x, "MCForward")
         lib = L.lib()
         self.net, self.group = net, group
@@ -87,7 +91,10 @@ class MCForward:
         self.seed = int(seed)
         B, Cc = self.B, self.C
         f32 = dict(dtype=torch.float32, device=dev)
-        self.x = example_x.clone()
+        self.inputs = list(static_inputs) if static_inputs else [example_x.clone()]
+        assert all(t.is_cuda and t.shape == example_x.shape and t.is_contiguous() for t in self.inputs)
+        self.x = self.inputs[0]
+        self.first_replay = int(first_replay)
         self.labels = torch.zeros(B, dtype=torch.int64, device=dev) if with_labels else None
         self.logits = torch.zeros(max(1, len(self.ids)), B, Cc, **f32)
         self.kl_one = torch.zeros((), **f32)
@@ -108,7 +115,7 @@ class MCForward:
             ptrs = self._open_peers(nbytes)
         self.peers = (C.c_void_p * self.world)(*ptrs)
         self.base = torch.zeros(1, dtype=torch.int64, device=dev)
-        self.graph = None
+        self.graph, self.graphs = None, []
         self.replays = 0
         self.kernels_per_step = None
         if graph:
@@ -185,27 +192,29 @@ class MCForward:
                 self._step(self.x, self.base)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
-        g = torch.cuda.CUDAGraph()
-        n0 = L.launch_count()
-        with torch.cuda.graph(g):
-            Fn.noise_advance(self.base, _STRIDE)
-            self._step(self.x, self.base)
-        self.kernels_per_step = L.launch_count() - n0
-        self.graph = g
-        self.base.fill_(-_STRIDE)
+        for xin in self.inputs:
+            g = torch.cuda.CUDAGraph()
+            n0 = L.launch_count()
+            with torch.cuda.graph(g):
+                Fn.noise_advance(self.base, _STRIDE)
+                self._step(xin, self.base)
+            self.kernels_per_step = L.launch_count() - n0          # engine kernels captured in one step
+            self.graphs.append(g)
+        self.graph = self.graphs[0]
+        self.base.fill_((self.first_replay - 1) * _STRIDE)
 
-    def __call__(self, x: Optional[torch.Tensor] = None, labels: Optional[torch.Tensor] = None):
+    def __call__(self, x: Optional[torch.Tensor] = None, labels: Optional[torch.Tensor] = None, slot: int = 0):
         if labels is not None:
             if self.labels is None:
                 raise L.EngineError("MCForward was built without with_labels=True")
             self.labels.copy_(labels, non_blocking=True)
         if self.graph is not None:
             if x is not None:
-                self.x.copy_(x, non_blocking=True)
-            self.graph.replay()
+                self.inputs[slot].copy_(x, non_blocking=True)
+            self.graphs[slot].replay()
             self.replays += 1
             return self.out
-        return self._step(self.x if x is None else x.to(self.dev))
+        return self._step(self.inputs[slot] if x is None else x.to(self.dev))
 
 
 def _generic_mc_forward(forward_fn: Callable, x: torch.Tensor, num_ens: int, group=None, want_uncertainty: bool = False):

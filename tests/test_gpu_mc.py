@@ -69,11 +69,13 @@ def test_mc_exchange_matches_oracle_single_and_emulated_ranks(dev):
     from oracle import bbb_oracle as O
     g = torch.Generator().manual_seed(2)
     for (S, B, Cc, world) in [(1, 5, 10, 1), (7, 33, 10, 3), (25, 64, 100, 8), (3, 700, 10, 4), (2, 9, 10, 4)]:
-        logits = torch.randn(S, B, Cc, generator=g) * 4
-        logits[0, 0, :] = torch.tensor([-200.0] * (Cc - 1) + [0.0])        # a class that underflows in fp32 softmax
+        base_logits = torch.randn(S, B, Cc, generator=g) * 4
         labels = torch.randint(0, Cc, (B,), generator=g)
         kl = 1234.5
         for normalized in (False, True):
+            logits = base_logits.clone()
+            if not normalized:        # classes whose softmax underflows fp32 in EVERY sample: logmeanexp must stay finite
+                logits[:, 0, :] = torch.tensor([-200.0] * (Cc - 1) + [0.0])
             per_rank = []
             for r in range(world):
                 ids = list(range(r, S, world))
