@@ -132,13 +132,6 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw32(uint32_t saddr, uint32_t
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (6ull << 61);
 }
 __device__ __forceinline__ uint32_t sw32(uint32_t addr) { return addr ^ (((addr >> 7) & 1u) << 4); }
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-                 ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
-                   "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])) : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
 template <int VARIANT>
 __global__ void __launch_bounds__(S4_THREADS, 1)
 conv_s4_kernel(const S4Args p) {
@@ -184,44 +177,77 @@ conv_s4_kernel(const S4Args p) {
     if (tr && threadIdx.x == 0) tr[1] = clock64();
 
     if (warp < 8) {
-        // ================= (1) stage the images ==============================================================
+        // ================= (1) stage the images, (2) draw the LRT noise -- interleaved =============================
+        // Both are latency problems (global loads / the serial Philox rounds), so each staging batch issues its loads,
+        // then a slice of the noise is computed while they are in flight, then the batch is converted and stored.
         const int t = threadIdx.x;
+        const int m = (warp & 3) * 32 + lane, half = warp >> 2;            // TMEM lane == tile row; 32 of the 64 columns
+        const int mi = m >> 3, ow = m & 7, b = img0 + mi;
+        const bool bvalid = b < g.B;
+        const bool philox = two && !p.eps_a;
+        // Noise goes to TENSOR MEMORY (columns behind the accumulators, this thread's lane): 64 values per thread would
+        // otherwise pin 64 registers and force the epilogue to be fully unrolled (register arrays cannot be indexed by a
+        // loop counter) -- straight-line code executed once per CTA, which is what the cold instruction cache punishes.
+        const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(half * 32);
+        const uint32_t noise_col = 256u;
+        const NoiseKey nkey = effective_key(p.key, p.stream_base);
+        auto noise_slice = [&](int it) {                                    // 16 of this thread's 64 normals: 4 independent Philox chains
+            const int ohl = it >> 1, k16 = it & 1;
+            float z[16];
+            if (bvalid) {
+                const uint64_t g0 = (((uint64_t)b * g.OHW + (uint64_t)((2 * ohp + ohl) * g.OW + ow)) * g.N + half * 32 + k16 * 16) >> 2;
+                const float4 za = normal4(g0, nkey), zb = normal4(g0 + 1, nkey), zc = normal4(g0 + 2, nkey), zd = normal4(g0 + 3, nkey);
+                z[0] = za.x; z[1] = za.y; z[2] = za.z; z[3] = za.w; z[4] = zb.x; z[5] = zb.y; z[6] = zb.z; z[7] = zb.w;
+                z[8] = zc.x; z[9] = zc.y; z[10] = zc.z; z[11] = zc.w; z[12] = zd.x; z[13] = zd.y; z[14] = zd.z; z[15] = zd.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) z[j] = 0.0f;
+            }
+            const float (&lo)[8] = *reinterpret_cast<const float (*)[8]>(&z[0]);
+            const float (&hi)[8] = *reinterpret_cast<const float (*)[8]>(&z[8]);
+            tmem_st8(lane_base + noise_col + (uint32_t)(ohl * 64 + k16 * 16), lo);
+            tmem_st8(lane_base + noise_col + (uint32_t)(ohl * 64 + k16 * 16 + 8), hi);
+        };
+
         const int groups = g.W >> 2;                                        // float4 groups per input row
-        const int n_data = S4_IMGS * p.rows * groups;
+        const int n_rows = S4_IMGS * p.rows;                                // staged rows of the tile (image-major)
         const int chunks_row = p.wp >> 1, data_c0 = p.lpad >> 1, data_c1 = (p.lpad + g.W) >> 1;
         const int zc = chunks_row - (data_c1 - data_c0);                     // halo chunks per row
-        const int n_zero = S4_IMGS * p.rows * zc;
         const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
         auto sptr = [&](uint32_t saddr) { return reinterpret_cast<uint4*>(sm + (sw32(saddr) - base)); };   // swizzled 16-byte slot
-        for (int it = t; it < n_zero; it += 256) {
+        for (int it = t; it < n_rows * zc; it += 256) {                     // zero halo columns
             const int rowi = it / zc, k = it - rowi * zc;
             const int chunk = k < data_c0 ? k : data_c1 + (k - data_c0);
             const uint32_t off = (uint32_t)rowi * rowb + (uint32_t)chunk * 16u;
             *sptr(imgx + off) = z4;
             if (two) *sptr(imgx2 + off) = z4;
         }
+        // thread -> (float4 group gq, row slot rs); it walks the staged rows rs, rs + rstep, ... (no divisions in the loop)
+        const int gq = t % groups, rs = t / groups, rstep = 256 / groups;
         const size_t chw = (size_t)g.Cin * g.HW;
-        constexpr int SB = 4;                                               // items in flight per thread: 12 independent 16-byte loads
+        constexpr int SB = 4;                                               // rows in flight per thread: 12 independent 16-byte loads
+        int rowi = rs, im = rs / p.rows, lr = rs - im * p.rows;
+        int nit = 0;
 #pragma unroll 1
-        for (int it0 = t; it0 < n_data; it0 += 256 * SB) {
+        for (; rowi < n_rows; ) {
             float4 c[SB][4];
             uint32_t off[SB];
 #pragma unroll
             for (int u = 0; u < SB; ++u) {
-                const int it = it0 + 256 * u;
-                const int gq = it % groups, rowi = it / groups;              // rowi = image * rows + staged row
-                const int i = rowi / p.rows, lr = rowi - i * p.rows;
-                const int ih = row0 + lr, b = img0 + i;
+                const int ih = row0 + lr, bb = img0 + im;
                 c[u][0] = c[u][1] = c[u][2] = c[u][3] = make_float4(0.f, 0.f, 0.f, 0.f);
-                off[u] = it < n_data ? (uint32_t)rowi * rowb + (uint32_t)(p.lpad + gq * 4) * 8u : 0xffffffffu;   // 16-byte aligned: lpad even
-                if (it < n_data && b < g.B && (unsigned)ih < (unsigned)g.H) {
-                    const float* src = p.x + (size_t)b * chw + (size_t)ih * g.W + gq * 4;
+                off[u] = rowi < n_rows ? (uint32_t)rowi * rowb + (uint32_t)(p.lpad + gq * 4) * 8u : 0xffffffffu;   // 16-byte aligned: lpad even
+                if (rowi < n_rows && bb < g.B && (unsigned)ih < (unsigned)g.H) {
+                    const float* src = p.x + (size_t)bb * chw + (size_t)ih * g.W + gq * 4;
                     c[u][0] = __ldg(reinterpret_cast<const float4*>(src));
                     if (g.Cin > 1) c[u][1] = __ldg(reinterpret_cast<const float4*>(src + g.HW));
                     if (g.Cin > 2) c[u][2] = __ldg(reinterpret_cast<const float4*>(src + 2 * g.HW));
                     if (g.Cin > 3) c[u][3] = __ldg(reinterpret_cast<const float4*>(src + 3 * g.HW));
                 }
+                rowi += rstep; lr += rstep;
+                while (lr >= p.rows) { lr -= p.rows; ++im; }
             }
+            if (philox && nit < 4) { noise_slice(nit); ++nit; }             // Philox math while the loads are in flight
 #pragma unroll
             for (int u = 0; u < SB; ++u) {
                 if (off[u] == 0xffffffffu) continue;
@@ -239,33 +265,9 @@ conv_s4_kernel(const S4Args p) {
         fence_proxy_async();                                                // generic-proxy stores -> visible to the tensor core
         mbar_arrive(smem_u32(&ctl->img_ready));
         if (tr && threadIdx.x == 0) tr[2] = clock64();
-
-        // ================= (2) this thread's LRT noise, drawn while the tensor core works =========================
-        const int m = (warp & 3) * 32 + lane, half = warp >> 2;            // TMEM lane == tile row; 32 of the 64 columns
-        const int i = m >> 3, ow = m & 7, b = img0 + i;
-        const bool bvalid = b < g.B;
-        const bool philox = two && !p.eps_a;
-        // Noise goes to TENSOR MEMORY (columns behind the accumulators, this thread's lane): 64 values per thread would
-        // otherwise pin 64 registers and force the epilogue to be fully unrolled (register arrays cannot be indexed by a
-        // loop counter) -- straight-line code executed once per CTA, which is what the cold instruction cache punishes.
-        const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(half * 32);
-        const uint32_t noise_col = 256u;
         if (philox) {
-            const NoiseKey nkey = effective_key(p.key, p.stream_base);
 #pragma unroll 1
-            for (int it = 0; it < 8; ++it) {
-                const int ohl = it >> 2, k8 = it & 3;
-                float z8[8];
-                if (bvalid) {
-                    const uint64_t o0 = ((uint64_t)b * g.OHW + (uint64_t)((2 * ohp + ohl) * g.OW + ow)) * g.N + half * 32 + k8 * 8;
-                    const float4 za = normal4(o0 >> 2, nkey), zb = normal4((o0 >> 2) + 1, nkey);   // N == 64: four channels per Philox call
-                    z8[0] = za.x; z8[1] = za.y; z8[2] = za.z; z8[3] = za.w; z8[4] = zb.x; z8[5] = zb.y; z8[6] = zb.z; z8[7] = zb.w;
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) z8[j] = 0.0f;
-                }
-                tmem_st8(lane_base + noise_col + (uint32_t)(ohl * 64 + k8 * 8), z8);
-            }
+            for (; nit < 4; ++nit) noise_slice(nit);                        // the rest, while the tensor core works
             tmem_st_wait();
         }
         if (tr && threadIdx.x == 0) tr[3] = clock64();
@@ -286,12 +288,13 @@ conv_s4_kernel(const S4Args p) {
 #pragma unroll
             for (int ohl = 0; ohl < 2; ++ohl) {
                 float am[8];
-                tmem_ld8(lane_base + (uint32_t)(ohl * p.planes * 64 + c8 * 8), am);
+                tmem_ld8_nowait(lane_base + (uint32_t)(ohl * p.planes * 64 + c8 * 8), am);
                 if (two) {
                     float av[8], e8[8];
-                    tmem_ld8(lane_base + (uint32_t)(ohl * 128 + 64 + c8 * 8), av);
-                    if (philox) tmem_ld8(lane_base + noise_col + (uint32_t)(ohl * 64 + c8 * 8), e8);
-                    else {
+                    tmem_ld8_nowait(lane_base + (uint32_t)(ohl * 128 + 64 + c8 * 8), av);
+                    if (philox) tmem_ld8_nowait(lane_base + noise_col + (uint32_t)(ohl * 64 + c8 * 8), e8);
+                    tmem_ld_wait();
+                    if (!philox) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
                             e8[j] = bvalid ? __ldg(p.eps_a + ((size_t)b * g.N + n0 + j) * g.OHW + (2 * ohp + ohl) * g.OW + ow) : 0.0f;
@@ -302,6 +305,7 @@ conv_s4_kernel(const S4Args p) {
                         am[j] = am[j] + ctl->bias[n0 + j] + fast_sqrt(var) * e8[j];
                     }
                 } else {
+                    tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 8; ++j) am[j] += ctl->bias[n0 + j];
                 }
@@ -326,10 +330,24 @@ conv_s4_kernel(const S4Args p) {
         tc_fence_before();
     } else if (warp == 8) {
         // ================= MMA issuer ================================================================================
+        // One thread issues every MMA, so the instructions BETWEEN two tcgen05.mma are the main loop's critical path
+        // (measured: ~20 dependent ALU instructions per MMA for descriptor arithmetic = ~115 cycles per 32-cycle MMA).
+        // Descriptors are linear in their 16-byte address field: build the four A bases and the B base once, step them
+        // by constants per kernel row, and add immediates per MMA.
         constexpr uint32_t idesc = make_idesc_bf16(128, 64);
+        const uint32_t arow_step = rowb >> 4;                                // one kernel row further down the staged image
+        uint64_t dA[2][2];                                                   // [output row of the pair][x | x^2], kernel row 0
+#pragma unroll
+        for (int ohl = 0; ohl < 2; ++ohl) {
+            dA[ohl][0] = make_smem_desc_sw32(imgx + (uint32_t)(ohl * g.SH) * rowb, imgb);
+            dA[ohl][1] = make_smem_desc_sw32(imgx2 + (uint32_t)(ohl * g.SH) * rowb, imgb);
+        }
+        const uint64_t dB0 = make_smem_desc(ring, 1024u, 128u);
+        const uint32_t acc1 = (uint32_t)(p.planes * 64);                     // accumulators of the second output row
         __syncwarp();
         mbar_wait(smem_u32(&ctl->img_ready), 0u);
         tc_fence_after();
+#pragma unroll 1
         for (int r = 0; r < g.KH; ++r) {
             const int s = r % S4_STAGES;
             __syncwarp();                                                   // converged whole-warp wait (single-lane waits wake late)
@@ -337,23 +355,21 @@ conv_s4_kernel(const S4Args p) {
             tc_fence_after();
             if (tr && lane == 0) tr[8 + r] = clock64();
             if (lane == 0) {
-                const uint32_t st = ring + (uint32_t)s * stage_bytes;
+                const uint64_t db = dB0 + (uint64_t)(((uint32_t)s * stage_bytes) >> 4);
+                const uint32_t acc = r ? 1u : 0u;
 #pragma unroll
-                for (int ohl = 0; ohl < 2; ++ohl) {
-                    const uint32_t arow = (uint32_t)(ohl * g.SH + r) * rowb;
-#pragma unroll
-                    for (int kc = 0; kc < 3; ++kc) {
-                        const uint64_t db = make_smem_desc(st + kc * 2048u, 1024u, 128u);
-                        umma_bf16(tmem + (uint32_t)(ohl * p.planes * 64), make_smem_desc_sw32(imgx + arow + kc * 32u, imgb), db, idesc, (r | kc) ? 1u : 0u);
-                        if (two) {
-                            const uint64_t db2 = make_smem_desc(st + S4_BPLANE + kc * 2048u, 1024u, 128u);
-                            umma_bf16(tmem + (uint32_t)(ohl * 128 + 64), make_smem_desc_sw32(imgx2 + arow + kc * 32u, imgb), db2, idesc, (r | kc) ? 1u : 0u);
-                        }
+                for (int kc = 0; kc < 3; ++kc) {
+                    umma_bf16(tmem, dA[0][0] + 2 * kc, db + 128 * kc, idesc, (acc | kc) ? 1u : 0u);
+                    umma_bf16(tmem + acc1, dA[1][0] + 2 * kc, db + 128 * kc, idesc, (acc | kc) ? 1u : 0u);
+                    if (two) {
+                        umma_bf16(tmem + 64u, dA[0][1] + 2 * kc, db + (S4_BPLANE >> 4) + 128 * kc, idesc, (acc | kc) ? 1u : 0u);
+                        umma_bf16(tmem + 192u, dA[1][1] + 2 * kc, db + (S4_BPLANE >> 4) + 128 * kc, idesc, (acc | kc) ? 1u : 0u);
                     }
                 }
                 umma_commit(smem_u32(&ctl->empty[s]));
                 if (r == g.KH - 1) umma_commit(smem_u32(&ctl->accum));
                 if (tr) tr[24 + r] = clock64();
+                dA[0][0] += arow_step; dA[0][1] += arow_step; dA[1][0] += arow_step; dA[1][1] += arow_step;
             }
             __syncwarp();
         }

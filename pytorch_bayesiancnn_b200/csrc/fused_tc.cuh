@@ -44,9 +44,6 @@ struct FusedArgs {
     long long* trace;            // debug: per-CTA clock64 checkpoints (nullptr in production)
     long long* tl_prep; long long* tl_gemm;   // debug: timeline slots of the two launches (nullptr in production)
     int units;                   // K blocks per pipeline step (TAP_UNITS, or 1 in the two-CTAs-per-SM LRT configuration)
-    int ez_smem;                 // LRT noise: 1 = drawn into shared memory during the main loop, 0 = drawn in the epilogue
-    int dbg_mma_j;               // debug: K-steps issued per stage (4 in production)
-    int dbg_mode;                // debug: bit0 skip weight copies, bit1 skip A copies, bit2 free stages with a plain arrive
 };
 
 __host__ __device__ inline size_t fused_wtile_elems(const FusedArgs& a) { return (size_t)a.planes * a.ng * 64; }
@@ -272,7 +269,6 @@ struct FusedSmem {
     // hand-off (~500-900 cycles measured: barrier round trip + TMA issue + first-MMA start-up) is paid per STEP.
     int2 items[TAP_MAX_ITEMS];
     int taps_px[64];                // per input pixel: packed taps (staging for the schedule build)
-    unsigned long long sq[4];       // SQ variant only: "A^2 of stage s is ready" (kept last: the other offsets do not move)
 };
 
 // tap linking output pixel (oh,ow) with input pixel (ih,iw); -1 if outside the kernel window
@@ -305,12 +301,22 @@ __device__ __forceinline__ float4 act_noise4(const NoiseKey& k, int b, int pix, 
 // elected thread each; the copies of a stage are dealt round-robin so their ~100-cycle issue costs overlap).
 constexpr int TAP_THREADS = 416, TAP_NPROD = 4;
 
-// SQ (experimental, BBB_B200_SQ_ONCHIP=1, LRT only): the activation arrives WITHOUT its x^2 blocks; the producer warp
-// that owns a stage squares the landed A tile into the stage's A^2 slot (element-wise, layout-agnostic: both tiles
-// share the SW128 image) and signals sq[s]; the MMA warp issues the mean MMAs first and the variance MMAs after sq[s].
-// Cuts the bytes a K block pulls through L2 from 48 KB to 32 KB and halves the activation traffic between layers.
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                   "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// TMEM columns of a tile: [0,64) mean accumulator, [64,128) variance accumulator (LRT), [128,192) the tile's LRT noise.
+// The noise tile is drawn (Philox) by the epilogue warps WHILE the main loop runs and parked in tensor memory: no
+// shared memory, no registers held across the main loop, and the epilogue stays a short rolled loop with static
+// register indices (a 64-value register array would force full unrolling; straight-line code that runs once per CTA
+// is what the cold instruction cache punishes -- DESIGN.md 5).
+constexpr uint32_t TAP_NOISE_COL = 128u;
+
 // MINB = resident CTAs per SM the register allocation is sized for (1: configuration A, 2: configuration B)
-template <int MINB, bool SQ = false>
+template <int MINB>
 __global__ void __launch_bounds__(TAP_THREADS, MINB)
 tap_gemm_kernel(const FusedArgs p, const int stages) {
     extern __shared__ uint8_t smem_raw[];
@@ -329,21 +335,16 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
     const int units = p.units;
     const uint32_t stage_bytes = (uint32_t)units * unit_bytes;
     const uint32_t a2_off = TC_A_BYTES, b_off = (uint32_t)planes * TC_A_BYTES;
-    float* ez = reinterpret_cast<float*>(sm + tiles_off + (size_t)stages * stage_bytes);   // [64][128] LRT noise
 
     // output tile -> (pixel set, cout block)
     const int n_tile = blockIdx.x, m0 = blockIdx.y * TC_BM;
     const int cb = n_tile % p.n_cblk, pset = n_tile / p.n_cblk;
-    int goh[4], gow[4];
-    if (p.pool) {
-        const int wy = pset / (g.OW >> 1), wx = pset - wy * (g.OW >> 1);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { goh[q] = 2 * wy + (q >> 1); gow[q] = 2 * wx + (q & 1); }
-    } else {
-        goh[0] = pset / g.OW; gow[0] = pset - goh[0] * g.OW;
-#pragma unroll
-        for (int q = 1; q < 4; ++q) { goh[q] = goh[0]; gow[q] = gow[0]; }
-    }
+    // pixel of column group q: pool -> the q-th pixel of the 2x2 window `pset`; otherwise the single pixel `pset`
+    const int win_y = p.pool ? pset / (g.OW >> 1) : 0, win_x = p.pool ? pset - win_y * (g.OW >> 1) : 0;
+    auto group_pix = [&](int q, int& oh, int& ow) {
+        if (p.pool) { oh = 2 * win_y + (q >> 1); ow = 2 * win_x + (q & 1); }
+        else { oh = pset / g.OW; ow = pset - oh * g.OW; }
+    };
 
     // debug trace: 128 slots per CTA -- [0,8) phase checkpoints, [8,40) MMA thread: full[s] passed at step it,
     // [48,88) producer 0: empty[s] passed at step it, [88,128) producer 0: step it issued
@@ -357,7 +358,6 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
             mbar_init(smem_u32(&ctl->empty[s]), 1);
         }
         mbar_init(smem_u32(&ctl->accum), 1);
-        if constexpr (SQ) for (int s = 0; s < stages; ++s) mbar_init(smem_u32(&ctl->sq[s]), 1);
         fence_barrier_init();
     }
     // K-loop schedule: one thread per input pixel works out the taps (integer divisions), thread 64 compacts
@@ -366,7 +366,9 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
         const int ih = ipix / g.W, iw = ipix - ih * g.W;
         uint32_t taps = 0;
         for (int q = 0; q < 4; ++q) {
-            const int tp = (q < groups) ? tap_of(g, goh[q], gow[q], ih, iw) : -1;
+            int oh, ow;
+            group_pix(q, oh, ow);
+            const int tp = (q < groups) ? tap_of(g, oh, ow, ih, iw) : -1;
             taps |= (uint32_t)(tp >= 0 ? tp : 0xFF) << (8 * q);
         }
         ctl->taps_px[ipix] = (int)taps;
@@ -381,9 +383,8 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
         }
         ctl->n_items = (uint32_t)n;
     }
-    // (A split of the K loop over two accumulator sets was tried -- the chain of dependent tcgen05.mma's is NOT
-    //  what bounds the main loop: it got 20 % slower.)
-    const uint32_t tmem_cols = two ? 128u : 64u;
+    const bool philox = two && !p.eps_a;
+    const uint32_t tmem_cols = philox ? 256u : (two ? 128u : 64u);
     if (warp == 8) tmem_alloc(smem_u32(&ctl->tmem_base), tmem_cols);
     tc_fence_before();
     __syncthreads();
@@ -410,9 +411,8 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
         const size_t sub_elems = (size_t)planes * ng * 64;
         const __nv_bfloat16* zero_tile = p.wtiles + (size_t)p.taps * p.n_cblk * p.n_kblk * sub_elems;
         const uint32_t gbytes = (uint32_t)ng * 128;                     // one group, one plane
-        const uint32_t a_copy = SQ ? (uint32_t)TC_A_BYTES : (uint32_t)planes * TC_A_BYTES;   // SQ: x only, x^2 formed here
-        const uint32_t unit_tx = ((p.dbg_mode & 2) ? 0u : a_copy) +
-                                 ((p.dbg_mode & 1) ? 0u : (uint32_t)(groups * planes) * gbytes);
+        const uint32_t a_copy = (uint32_t)planes * TC_A_BYTES;
+        const uint32_t unit_tx = a_copy + (uint32_t)(groups * planes) * gbytes;
         const size_t a_row0 = (size_t)blockIdx.y * (p.in_pitch >> 6);   // first 16 KB block of this row tile
 #pragma unroll 1
         for (int it = pid; it < n_steps && pid < nprod; it += nprod) {
@@ -430,46 +430,24 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
                     const int ipix = item.x & 0xffff, kb = item.x >> 16;
                     const uint32_t st = base + tiles_off + (uint32_t)s * stage_bytes + (uint32_t)u * unit_bytes;
                     // x and x^2 blocks are interleaved in global memory and adjacent in the stage: one copy
-                    const size_t a_blk = (a_row0 + (size_t)ipix * p.n_kblk + kb) * (size_t)((SQ ? 1 : planes) * 128 * 64);
-                    if (!(p.dbg_mode & 2))
-                        bulk_g2s(st, reinterpret_cast<const __nv_bfloat16*>(p.x) + a_blk, a_copy, bar);
-                    if (!(p.dbg_mode & 1)) {
-                        // weight planes: [plane][group][ng rows x 128 B] -> every plane is one 64-row SW128 tile
+                    const size_t a_blk = (a_row0 + (size_t)ipix * p.n_kblk + kb) * (size_t)(planes * 128 * 64);
+                    bulk_g2s(st, reinterpret_cast<const __nv_bfloat16*>(p.x) + a_blk, a_copy, bar);
+                    // weight planes: [plane][group][ng rows x 128 B] -> every plane is one 64-row SW128 tile
 #pragma unroll 1
-                        for (int q = 0; q < groups; ++q) {
-                            const int tp = (item.y >> (8 * q)) & 0xFF;
-                            const __nv_bfloat16* sp = tp != 0xFF ? p.wtiles + ((size_t)(tp * p.n_cblk + cb) * p.n_kblk + kb) * sub_elems : zero_tile;
-                            if (groups == 1) {           // [mu | sigma^2] of the sub-tile are contiguous here and in the stage
-                                bulk_g2s(st + b_off, sp, (uint32_t)planes * gbytes, bar);
-                            } else {
-                                bulk_g2s(st + b_off + q * gbytes, sp, gbytes, bar);
-                                if (two) bulk_g2s(st + b_off + TC_B_BYTES + q * gbytes, tp != 0xFF ? sp + ng * 64 : zero_tile, gbytes, bar);
-                            }
+                    for (int q = 0; q < groups; ++q) {
+                        const int tp = (item.y >> (8 * q)) & 0xFF;
+                        const __nv_bfloat16* sp = tp != 0xFF ? p.wtiles + ((size_t)(tp * p.n_cblk + cb) * p.n_kblk + kb) * sub_elems : zero_tile;
+                        if (groups == 1) {           // [mu | sigma^2] of the sub-tile are contiguous here and in the stage
+                            bulk_g2s(st + b_off, sp, (uint32_t)planes * gbytes, bar);
+                        } else {
+                            bulk_g2s(st + b_off + q * gbytes, sp, gbytes, bar);
+                            if (two) bulk_g2s(st + b_off + TC_B_BYTES + q * gbytes, tp != 0xFF ? sp + ng * 64 : zero_tile, gbytes, bar);
                         }
                     }
                 }
                 if (tr && it < 40) tr[88 + it] = clock64();
             }
             __syncwarp();                                // stay converged: the next blocking wait must be a whole-warp wait
-            if constexpr (SQ) {
-                // this warp owns stage s: wait for its data, square A into the A^2 slot, tell the MMA warp
-                mbar_wait(smem_u32(&ctl->full[s]), (uint32_t)(it / stages) & 1u);
-                const int nu = min(units, n_items - it * units);
-                for (int u = 0; u < nu; ++u) {
-                    uint8_t* a_tile = sm + tiles_off + (size_t)s * stage_bytes + (size_t)u * unit_bytes;
-#pragma unroll 4
-                    for (int c = lane; c < TC_A_BYTES / 16; c += 32) {
-                        const uint4 v = *reinterpret_cast<const uint4*>(a_tile + c * 16);
-                        uint4 q;
-                        q.x = bf16x2_sq(v.x); q.y = bf16x2_sq(v.y); q.z = bf16x2_sq(v.z); q.w = bf16x2_sq(v.w);
-                        *reinterpret_cast<uint4*>(a_tile + a2_off + c * 16) = q;
-                    }
-                }
-                fence_proxy_async();                     // generic-proxy stores -> visible to the tensor core
-                __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&ctl->sq[s]));
-                __syncwarp();
-            }
         }
     } else if (warp == 8) {
         // ======================= MMA issuer =====================================
@@ -493,31 +471,11 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
                     const uint64_t da = dA0 + so, db = dB0 + so;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        if (j >= p.dbg_mma_j) break;
                         umma_bf16(tmem, da + 2 * j, db + 2 * j, idesc, (it | u | j) ? 1u : 0u);
-                        if (!SQ && two) umma_bf16(tmem + 64u, da + (a2_off >> 4) + 2 * j, db + (TC_B_BYTES >> 4) + 2 * j, idesc, (it | u | j) ? 1u : 0u);
+                        if (two) umma_bf16(tmem + 64u, da + (a2_off >> 4) + 2 * j, db + (TC_B_BYTES >> 4) + 2 * j, idesc, (it | u | j) ? 1u : 0u);
                     }
                 }
-                if constexpr (!SQ) {
-                    if (p.dbg_mode & 4) mbar_arrive(smem_u32(&ctl->empty[s])); else umma_commit(smem_u32(&ctl->empty[s]));
-                }
-            }
-            if constexpr (SQ) {                          // variance MMAs once the squared tiles of this stage are in place
-                __syncwarp();
-                mbar_wait(smem_u32(&ctl->sq[s]), (uint32_t)(it / stages) & 1u);      // whole-warp wait
-                tc_fence_after();
-                if (lane == 0) {
-                    const int nu = min(units, n_items - it * units);
-#pragma unroll 1
-                    for (int u = 0; u < nu; ++u) {
-                        const uint32_t so = ((uint32_t)s * stage_bytes + (uint32_t)u * unit_bytes) >> 4;
-                        const uint64_t da = dA0 + so, db = dB0 + so;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            umma_bf16(tmem + 64u, da + (a2_off >> 4) + 2 * j, db + (TC_B_BYTES >> 4) + 2 * j, idesc, (it | u | j) ? 1u : 0u);
-                    }
-                    umma_commit(smem_u32(&ctl->empty[s]));
-                }
+                umma_commit(smem_u32(&ctl->empty[s]));
             }
             __syncwarp();
         }
@@ -526,24 +484,31 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
         tc_fence_before();
     } else {
         // ======================= epilogue (warps 0-7) ===========================
+        // thread = (tile row t = image, half h); it owns four chunks of 8 columns: chunk k starts at tile column
+        //   pool: k*16 + h*8  (pixel k of the 2x2 window, channels h*8 .. h*8+7 of the tile's 16)
+        //   else: h*32 + k*8  (the tile's single pixel, channels h*32 + k*8 ..)
         const int t = threadIdx.x & 127, h = threadIdx.x >> 7, b = m0 + t;
         const bool bvalid = b < g.B;
-        const bool philox = two && !p.eps_a;
-        // column c of the tile belongs to group h iff own(c): pool: channel (c & 15) >> 3 == h, else c >> 5 == h
-        // (1) while the main loop runs: draw this row's LRT noise into smem (column-major, conflict free)
-        const NoiseKey nkey = effective_key(p.key, p.stream_base);
-        if (philox && bvalid && p.ez_smem) {
+        const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        const int n_base = p.pool ? cb * 16 + h * 8 : cb * 64 + h * 32;          // first output channel of chunk 0
+        // (1) while the main loop runs: draw this row's LRT noise and park it in tensor memory
+        if (philox) {
+            const NoiseKey nkey = effective_key(p.key, p.stream_base);
 #pragma unroll 1
-            for (int c4 = 0; c4 < 16; ++c4) {
-                const int c = c4 * 4;
-                if ((p.pool ? ((c & 15) >> 3) : (c >> 5)) != h) continue;
-                const int q = p.pool ? (c >> 4) : 0;
-                const int n = p.pool ? (cb * 16 + (c & 15)) : (cb * 64 + c);
-                float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (n < g.N) z = act_noise4(nkey, b, goh[q] * g.OW + gow[q], n, g.OHW, g.N);
-                ez[(c + 0) * 128 + t] = z.x; ez[(c + 1) * 128 + t] = z.y;
-                ez[(c + 2) * 128 + t] = z.z; ez[(c + 3) * 128 + t] = z.w;
+            for (int k = 0; k < 4; ++k) {
+                int oh, ow;
+                group_pix(k, oh, ow);
+                const int n0 = p.pool ? n_base : n_base + k * 8;
+                float z8[8];
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (bvalid && n0 + 4 * hh < g.N) z = act_noise4(nkey, b, oh * g.OW + ow, n0 + 4 * hh, g.OHW, g.N);
+                    z8[4 * hh] = z.x; z8[4 * hh + 1] = z.y; z8[4 * hh + 2] = z.z; z8[4 * hh + 3] = z.w;
+                }
+                tmem_st8(lane_base + TAP_NOISE_COL + (uint32_t)(p.pool ? k * 16 + h * 8 : h * 32 + k * 8), z8);
             }
+            tmem_st_wait();
         }
         const bool any_mma = n_items > 0;  // did the schedule of warp 8 contain at least one step?
         // (2) accumulator ready
@@ -558,74 +523,43 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
         mbar_wait(smem_u32(&ctl->accum), 0u);
         tc_fence_after();
         if (tr && threadIdx.x == 0) tr[5] = clock64();
-        const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         const int ohw_out = p.pool ? (g.OHW >> 2) : g.OHW;
-        const int n_base = p.pool ? cb * 16 : cb * 64;
-        const int i_begin = p.pool ? h : 4 * h, i_end = p.pool ? h + 1 : 4 * h + 4;   // groups of 8 output channels
+        float r[8];
 #pragma unroll 1
-        for (int i8 = i_begin; i8 < i_end; ++i8) {
-            float r[8];
-            if (p.pool) {
+        for (int k = 0; k < 4; ++k) {
+            const int c0 = p.pool ? k * 16 + h * 8 : h * 32 + k * 8;          // tile column of this chunk
+            const int n0 = p.pool ? n_base : n_base + k * 8;                  // its first output channel
+            float am[8];
+            tmem_ld8(lane_base + (uint32_t)c0, am);
+            if (two) {
+                float av[8], e8[8];
+                tmem_ld8(lane_base + 64u + (uint32_t)c0, av);
+                if (philox) tmem_ld8(lane_base + TAP_NOISE_COL + (uint32_t)c0, e8);
+                else {
+                    int oh, ow;
+                    group_pix(k, oh, ow);
 #pragma unroll
-                for (int u = 0; u < 8; ++u) r[u] = -INFINITY;
-#pragma unroll 1
-                for (int q = 0; q < 4; ++q) {
-                    const int c = q * 16 + i8 * 8;
-                    float am[8], av[8], zi[8];
-                    tmem_ld8(lane_base + (uint32_t)c, am);
-                    if (two) tmem_ld8(lane_base + 64u + (uint32_t)c, av);
-                    if (philox && !p.ez_smem) {
-                        const int n8 = n_base + i8 * 8;
-#pragma unroll
-                        for (int hh = 0; hh < 2; ++hh) {
-                            float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (bvalid && n8 + 4 * hh < g.N) z = act_noise4(nkey, b, goh[q] * g.OW + gow[q], n8 + 4 * hh, g.OHW, g.N);
-                            zi[4 * hh] = z.x; zi[4 * hh + 1] = z.y; zi[4 * hh + 2] = z.z; zi[4 * hh + 3] = z.w;
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        float val = (any_mma ? am[u] : 0.0f) + ctl->bias[c + u];
-                        if (two) {
-                            const float var = 1e-16f + ((any_mma ? av[u] : 0.0f) + ctl->bvar[c + u]);
-                            float e_ = 0.0f;
-                            if (philox) e_ = p.ez_smem ? ez[(c + u) * 128 + t] : zi[u];
-                            else if (bvalid && n_base + i8 * 8 + u < g.N)
-                                e_ = __ldg(p.eps_a + ((size_t)b * g.N + n_base + i8 * 8 + u) * g.OHW + goh[q] * g.OW + gow[q]);
-                            val = val + fast_sqrt(var) * e_;
-                        }
-                        r[u] = fmaxf(r[u], val);
-                    }
-                }
-            } else {
-                const int c = i8 * 8;
-                float am[8], av[8], zi[8];
-                tmem_ld8(lane_base + (uint32_t)c, am);
-                if (two) tmem_ld8(lane_base + 64u + (uint32_t)c, av);
-                if (philox && !p.ez_smem) {
-#pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (bvalid && n_base + c + 4 * hh < g.N) z = act_noise4(nkey, b, pset, n_base + c + 4 * hh, g.OHW, g.N);
-                        zi[4 * hh] = z.x; zi[4 * hh + 1] = z.y; zi[4 * hh + 2] = z.z; zi[4 * hh + 3] = z.w;
-                    }
+                    for (int u = 0; u < 8; ++u)
+                        e8[u] = (bvalid && n0 + u < g.N) ? __ldg(p.eps_a + ((size_t)b * g.N + n0 + u) * g.OHW + oh * g.OW + ow) : 0.0f;
                 }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    float val = (any_mma ? am[u] : 0.0f) + ctl->bias[c + u];
-                    if (two) {
-                        const float var = 1e-16f + ((any_mma ? av[u] : 0.0f) + ctl->bvar[c + u]);
-                        float e_ = 0.0f;
-                        if (philox) e_ = p.ez_smem ? ez[(c + u) * 128 + t] : zi[u];
-                        else if (bvalid && n_base + c + u < g.N)
-                            e_ = __ldg(p.eps_a + ((size_t)b * g.N + n_base + c + u) * g.OHW + pset);
-                        val = val + fast_sqrt(var) * e_;
-                    }
-                    r[u] = val;
+                    const float var = 1e-16f + ((any_mma ? av[u] : 0.0f) + ctl->bvar[c0 + u]);
+                    am[u] = (any_mma ? am[u] : 0.0f) + ctl->bias[c0 + u] + fast_sqrt(var) * e8[u];
                 }
+            } else {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) am[u] = (any_mma ? am[u] : 0.0f) + ctl->bias[c0 + u];
+            }
+            if (p.pool) {                                 // 2x2 max over the four chunks, store after the last
+#pragma unroll
+                for (int u = 0; u < 8; ++u) r[u] = k ? fmaxf(r[u], am[u]) : am[u];
+                if (k < 3) continue;
+            } else {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) r[u] = am[u];
             }
             if (!bvalid) continue;
-            const int n0 = n_base + i8 * 8;
 #pragma unroll
             for (int u = 0; u < 8; ++u) r[u] = fast_act(r[u], p.act);       // act is monotone: act(max) == max(act)
             if (p.out_mode == OUT_PACKED_BF16) {          // tiled packed (N % 64 == 0 guaranteed by the host)
@@ -680,14 +614,7 @@ inline cudaError_t launch_fused(FusedArgs a, const void* x, const void* x_sq, cu
     a.taps = g.KHW;
     const bool lrt = a.variant == BBB_VARIANT_LRT;
     a.x = x; a.x_sq = x_sq;
-    // experimental (not yet validated on hardware): LRT input arrives without x^2 blocks, squares formed on chip
-    static const bool sq_env = [] { const char* e = getenv("BBB_B200_SQ_ONCHIP"); return e && e[0] == '1'; }();
-    const bool sq = sq_env && a.planes == 2;
-    if (do_gemm && sq && x_sq != nullptr) {
-        *why = "BBB_B200_SQ_ONCHIP: the LRT activation must come without x^2 blocks (x_sq == NULL)";
-        return cudaErrorInvalidValue;
-    }
-    if (do_gemm && !sq && a.planes == 2 && x_sq != (const void*)((const __nv_bfloat16*)x + 128 * 64)) {
+    if (do_gemm && a.planes == 2 && x_sq != (const void*)((const __nv_bfloat16*)x + 128 * 64)) {
         *why = "LRT fused layer needs the activation with interleaved x / x^2 blocks (x_sq == x + 8192 elements)";
         return cudaErrorInvalidValue;
     }
@@ -733,47 +660,27 @@ inline cudaError_t launch_fused(FusedArgs a, const void* x, const void* x_sq, cu
         *n_launch += 1;
     }
     if (!do_gemm) return cudaSuccess;
-    a.dbg_mma_j = 4; a.dbg_mode = 0;
-    if (const char* e = getenv("BBB_B200_DBG_MODE")) a.dbg_mode = atoi(e);
-    if (const char* e = getenv("BBB_B200_DBG_MMAJ")) a.dbg_mma_j = atoi(e);
-    // Two configurations.  (A) one CTA per SM: stage = 2 K blocks, deep ring, LRT noise pre-drawn into 32 KB of smem.
-    // (B) two CTAs per SM (~99 KB each): used when the grid has more CTAs than SMs (AlexNet conv2: 192), so that all
-    // tiles run in ONE wave and one CTA's epilogue overlaps the other's main loop; LRT then draws its noise in the epilogue.
+    // Two configurations.  (A) one CTA per SM: stage = 2 K blocks, deep ring.  (B) two CTAs per SM (~99 KB each): used when
+    // the grid has more CTAs than SMs (AlexNet conv2: 192), so that all tiles run in ONE wave and one CTA's epilogue
+    // overlaps the other's main loop.  In both the LRT noise tile is drawn into tensor memory during the main loop.
     const int psets = a.pool ? (g.OH / 2) * (g.OW / 2) : g.OHW;
     const long n_ctas = (long)psets * a.n_cblk * ((g.B + TC_BM - 1) / TC_BM);
     const bool two_per_sm = n_ctas > n_sm;
     int stages;
-    if (two_per_sm) { stages = 2; a.units = a.planes == 2 ? 1 : 2; a.ez_smem = 0; }
-    else            { stages = a.planes == 2 ? 2 : 4; a.units = TAP_UNITS; a.ez_smem = 1; }
-    // experiment knobs: BBB_B200_UNITS=1 -> configuration A with one K block per stage and four stages (same
-    // shared-memory footprint for LRT, finer-grained hand-offs); BBB_B200_STAGES lowers the ring depth
-    if (const char* e = getenv("BBB_B200_UNITS")) { if (atoi(e) == 1 && !two_per_sm) { a.units = 1; stages = 4; } }
+    if (two_per_sm) { stages = 2; a.units = a.planes == 2 ? 1 : 2; }
+    else            { stages = a.planes == 2 ? 2 : 4; a.units = TAP_UNITS; }
     if (const char* e = getenv("BBB_B200_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= stages) stages = v; }
-    const size_t smem = 1023 + 2048 + (size_t)stages * a.units * tc_stage_bytes(a.planes) + ((a.planes == 2 && a.ez_smem) ? 64 * 128 * 4 : 0);   // align slack + control/schedule + ring + LRT noise tile
+    const size_t smem = 1023 + 2048 + (size_t)stages * a.units * tc_stage_bytes(a.planes);   // align slack + control/schedule + ring
     dim3 grid(psets * a.n_cblk, (g.B + TC_BM - 1) / TC_BM);
     cudaError_t e;
-    if (sq) {
-        auto launch = [&](auto kernel) {
-            cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            cudaError_t e2 = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e2 != cudaSuccess) return e2;
-            return launch_pdl(kernel, grid, dim3(TAP_THREADS), smem, st, a, stages);
-        };
-        e = two_per_sm ? launch(tap_gemm_kernel<2, true>) : launch(tap_gemm_kernel<1, true>);
-        if (e != cudaSuccess) return e;
-    } else if (two_per_sm) {
-        cudaFuncSetAttribute(tap_gemm_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        e = cudaFuncSetAttribute(tap_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        e = launch_pdl(tap_gemm_kernel<2>, grid, dim3(TAP_THREADS), smem, st, a, stages);
-        if (e != cudaSuccess) return e;
-    } else {
-        cudaFuncSetAttribute(tap_gemm_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        e = cudaFuncSetAttribute(tap_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        e = launch_pdl(tap_gemm_kernel<1>, grid, dim3(TAP_THREADS), smem, st, a, stages);
-        if (e != cudaSuccess) return e;
-    }
+    auto launch = [&](auto kernel) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaError_t e2 = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e2 != cudaSuccess) return e2;
+        return launch_pdl(kernel, grid, dim3(TAP_THREADS), smem, st, a, stages);
+    };
+    e = two_per_sm ? launch(tap_gemm_kernel<2>) : launch(tap_gemm_kernel<1>);
+    if (e != cudaSuccess) return e;
     e = cudaGetLastError();
     if (e == cudaSuccess) *n_launch += 1;
     return e;

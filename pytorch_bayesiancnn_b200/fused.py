@@ -167,12 +167,6 @@ def _side_stream(dev, i=0):
     return st
 
 
-def _sq_onchip():
-    """Experimental (csrc/fused_tc.cuh, tap_gemm_kernel<.., SQ=true>): LRT consumers square the activation tile
-    on chip, so producers write x only."""
-    return os.environ.get("BBB_B200_SQ_ONCHIP", "0") == "1"
-
-
 def _prep_chains():
     return max(1, int(os.environ.get("BBB_B200_PREP_CHAINS", "3")))
 
@@ -269,7 +263,7 @@ def run_step(st, nxt, cur, cur_sq, cur_pitch, kl=None, noise=None, phase=0):
             pitch, y, y_sq = cout * oh * ow if st.out_layout == L.LAYOUT_PACKED_BF16 else 0, None, None
         elif st.out_layout == L.LAYOUT_PACKED_BF16:
             pitch = cout * oh * ow                   # tiled packed: [ceil(B/128)][F/64][planes][128 x 64] bf16
-            planes = 2 if (nxt is not None and nxt._variant == L.VARIANT_LRT and not _sq_onchip()) else 1
+            planes = 2 if (nxt is not None and nxt._variant == L.VARIANT_LRT) else 1
             y = torch.empty((B + 127) // 128 * 128, pitch * planes, dtype=torch.bfloat16, device=dev)
             y_sq = y.view(-1)[128 * 64:] if planes == 2 else None      # x^2 blocks interleaved behind the x blocks
         elif st.out_layout == L.LAYOUT_ROWMAJOR_F32:

@@ -92,7 +92,7 @@ def test_mc_exchange_matches_oracle_single_and_emulated_ranks(dev):
                 assert torch.isfinite(o["lo"]).all()
                 assert (o["lo"].double().cpu() - ref).abs().max() < 2e-5 * max(1.0, float(ref.abs().max())), (S, B, Cc, world)
                 assert abs(float(o["kl"]) - kl) < 1e-3                       # sum_j kl_j / S == kl (main_bayesian.py:51)
-                assert (o["pred"].double().cpu() - pred).abs().max() < 1e-5
+                assert (o["pred"].double().cpu() - pred).abs().max() < 2e-6 * max(1.0, float(pred.abs().max())) * S
                 assert (o["epi"].double().cpu() - epi).abs().max() < 2e-6
                 assert (o["ale"].double().cpu() - ale).abs().max() < 2e-6
                 assert (o["ent"].double().cpu() - ent).abs().max() < 1e-5
