@@ -133,7 +133,12 @@ enum { BBB_LAYOUT_NCHW_F32 = 0,      /* reference layout: [B, C, H, W] fp32     
  * desc->reserved[0] splits the call so the parameter-only half can run on a side stream, off
  * the activation critical path: BBB_FUSED_PREP_ONLY launches just the weight-prep kernel
  * (sigma, eps, bf16 operand tiles, KL -> kl_out; x/y unused), BBB_FUSED_SKIP_PREP just the GEMM
- * kernel (the caller orders it after the prep, e.g. with an event).  0 = both, in order. */
+ * kernel (the caller orders it after the prep, e.g. with an event).  0 = both, in order.
+ * desc->reserved[1] > 0 folds Monte-Carlo samples into the batch (LRT + Philox only; what
+ * uncertainty_estimation.py:38-41 does by repeating the input): row b of the batch is image b % reserved[1] of sample
+ * b / reserved[1], whose noise comes from Philox stream stream_id + (b / reserved[1]) * stride, stride = the uint64
+ * in reserved[2] (low) / reserved[3] (high) -- bit-identical to separate calls per sample.  The NCHW input of the
+ * first layer then holds reserved[1] images (it is not repeated). */
 enum { BBB_FUSED_PREP_ONLY = 1, BBB_FUSED_SKIP_PREP = 2 };
 int bbb_layer_forward_fused(const bbb_layer_desc* desc,
                             const void* x, const void* x_sq, int32_t in_layout, int32_t in_pitch, int32_t prev_hw,
@@ -219,14 +224,19 @@ int bbb_mc_combine(const float* logits, int32_t S, int32_t B, int32_t C,
  * peer_buffers: HOST array of `world` device pointers, one receive buffer per rank (bbb_mc_buffer_bytes each, zero-
  *   filled once; [rank] is the local one; with world == 1 any device allocation will do);
  * state: local device scratch of bbb_mc_state_bytes(), zero-filled once.  Sequence numbers inside make the buffers
- * reusable call after call (and CUDA-graph replay after replay) with no reset.  Every rank must make the same calls. */
+ * reusable call after call (and CUDA-graph replay after replay) with no reset.  Every rank must make the same calls.
+ * kl: n_kl device floats whose SUM is one sample's KL (e.g. the per-layer scalars the layer calls wrote: the sum over
+ *   layers of ModuleWrapper.forward, layers/misc.py:21-23, happens here); n_kl <= 0 means 1.
+ * noise_base (nullable): *noise_base += noise_inc when the launch has finished -- the last kernel of a captured step
+ *   moves the Philox stream base for the next replay (replaces a leading bbb_noise_advance launch). */
 enum { BBB_MC_MOMENTS = 1, BBB_MC_NORMALIZED = 2 };
 size_t bbb_mc_buffer_bytes(int32_t B, int32_t C, int32_t flags, int32_t world);
 size_t bbb_mc_state_bytes(void);
 int bbb_mc_exchange(const float* logits, int32_t S_local, int32_t S_total, int32_t B, int32_t C, const float* kl,
-                    int32_t flags, const int64_t* labels, float train_size, float beta, int32_t rank, int32_t world,
-                    void* const* peer_buffers, void* state, float* log_outputs, float* kl_out, float* pred,
-                    float* epistemic, float* aleatoric, float* entropy, float* head, void* cuda_stream);
+                    int32_t n_kl, int32_t flags, const int64_t* labels, float train_size, float beta, int32_t rank,
+                    int32_t world, void* const* peer_buffers, void* state, float* log_outputs, float* kl_out, float* pred,
+                    float* epistemic, float* aleatoric, float* entropy, float* head, uint64_t* noise_base,
+                    uint64_t noise_inc, void* cuda_stream);
 
 /* Peer-mapped receive buffers for bbb_mc_exchange (one process per GPU, same node): allocate locally, export a
  * 64-byte CUDA-IPC handle, ship it to the peers by any host channel (the Python side uses torch.distributed),

@@ -83,8 +83,8 @@ def _bind(lib):
     lib.bbb_mc_buffer_bytes.restype = sz
     lib.bbb_mc_state_bytes.argtypes = []
     lib.bbb_mc_state_bytes.restype = sz
-    lib.bbb_mc_exchange.argtypes = [fp, i32, i32, i32, i32, fp, i32, vp, C.c_float, C.c_float, i32, i32,
-                                    C.POINTER(C.c_void_p), vp, fp, fp, fp, fp, fp, fp, fp, vp]
+    lib.bbb_mc_exchange.argtypes = [fp, i32, i32, i32, i32, fp, i32, i32, vp, C.c_float, C.c_float, i32, i32,
+                                    C.POINTER(C.c_void_p), vp, fp, fp, fp, fp, fp, fp, fp, vp, u64, vp]
     lib.bbb_mc_exchange.restype = C.c_int
     lib.bbb_comm_alloc.argtypes = [sz, C.POINTER(C.c_void_p)]
     lib.bbb_comm_export.argtypes = [vp, vp]

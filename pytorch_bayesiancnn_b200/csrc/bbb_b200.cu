@@ -238,6 +238,14 @@ int bbb_layer_forward_fused(const bbb_layer_desc* d, const void* x, const void* 
     if (!W_mu || !W_rho || (!prep_only && (!x || !y))) return fail(BBB_E_INVALID, "NULL tensor pointer");
     if (d->has_bias && (!bias_mu || !bias_rho)) return fail(BBB_E_INVALID, "has_bias set but bias pointers NULL");
     const int pool = d->pool_k != 0;
+    bbb::McFold fold; fold.rows = 0; fold.stride = 0;
+    if (d->reserved[1] > 0) {           // MC samples folded into the batch
+        if (d->variant != BBB_VARIANT_LRT || !d->sample || eps_a)
+            return fail(BBB_E_UNSUPPORTED, "MC-sample folding needs the LRT variant with in-kernel Philox noise");
+        if (g.B % d->reserved[1]) return fail(BBB_E_INVALID, "batch %d is not a multiple of the rows per MC sample %d", g.B, d->reserved[1]);
+        fold.rows = d->reserved[1];
+        fold.stride = ((unsigned long long)(uint32_t)d->reserved[3] << 32) | (uint32_t)d->reserved[2];
+    }
     const size_t need = bbb_workspace_bytes(d);
     if (!ws || ws_bytes < need) return fail(BBB_E_WORKSPACE, "workspace too small for the fused path: need %zu bytes", need);
     if (out_layout == BBB_LAYOUT_PACKED_BF16 && y_sq && y_sq != (void*)((__nv_bfloat16*)y + 128 * 64))
@@ -258,11 +266,12 @@ int bbb_layer_forward_fused(const bbb_layer_desc* d, const void* x, const void* 
         a.variant = d->variant; a.out_pitch = out_pitch;
         a.wtiles = (__nv_bfloat16*)((char*)ws + kTcOffset);
         a.bias_ws = (float*)((char*)ws + kTcOffset + (size_t)g.KH * 2 * bbb::S4_BPLANE);
-        a.trace = g_trace;
+        a.trace = g_trace; a.fold = fold;
         a.tl_prep = tl_slot(!skip_prep, "conv_s4_prep", g); a.tl_gemm = tl_slot(!prep_only, "conv_s4", g);
         cudaError_t e = bbb::launch_conv_s4(a, st, !skip_prep, !prep_only, &nl);
         if (e != cudaSuccess) return cuda_fail(e, "conv_s4 launch");
     } else if (in_layout == BBB_LAYOUT_NCHW_F32) {
+        if (fold.rows) return fail(BBB_E_UNSUPPORTED, "MC-sample folding is not available on the gather path");
         bbb::TcArgs a;
         a.g = g; a.x = x; a.w_mu = W_mu; a.w_rho = W_rho; a.b_mu = bias_mu; a.b_rho = bias_rho;
         a.y = y; a.kl_out = kl_out; a.act_std = nullptr; a.eps_a = eps_a; a.eps_b = eps_b;
@@ -288,7 +297,7 @@ int bbb_layer_forward_fused(const bbb_layer_desc* d, const void* x, const void* 
         a.wtiles = (__nv_bfloat16*)((char*)ws + kTcOffset);
         a.bias_ws = (float*)((char*)ws + kTcOffset + cpad * kpad * g.KHW * 4 + 16384);   // behind the zero sub-tile
         a.prev_hw = prev_hw; a.y = y; a.y_sq = y_sq; a.out_mode = out_mode; a.out_pitch = out_pitch; a.pool = pool;
-        a.in_pitch = in_pitch; a.trace = g_trace;
+        a.in_pitch = in_pitch; a.trace = g_trace; a.fold = fold;
         a.tl_prep = tl_slot(!skip_prep, "tap_prep", g); a.tl_gemm = tl_slot(!prep_only, "tap_gemm", g);
         const char* why = "";
         cudaError_t e = bbb::launch_fused(a, x, x_sq, st, &nl, &why, !skip_prep, !prep_only, sm_count());
@@ -370,9 +379,10 @@ size_t bbb_mc_buffer_bytes(int32_t B, int32_t C, int32_t flags, int32_t world) {
 size_t bbb_mc_state_bytes(void) { return 64 + (size_t)bbb::MCX_MAX_CTAS * 2 * sizeof(double); }
 
 int bbb_mc_exchange(const float* logits, int32_t S_local, int32_t S_total, int32_t B, int32_t C, const float* kl,
-                    int32_t flags, const int64_t* labels, float train_size, float beta, int32_t rank, int32_t world,
+                    int32_t n_kl, int32_t flags, const int64_t* labels, float train_size, float beta, int32_t rank, int32_t world,
                     void* const* peer_buffers, void* state, float* log_outputs, float* kl_out, float* pred,
-                    float* epistemic, float* aleatoric, float* entropy, float* head, void* cuda_stream) {
+                    float* epistemic, float* aleatoric, float* entropy, float* head, uint64_t* noise_base,
+                    uint64_t noise_inc, void* cuda_stream) {
     if (!log_outputs || !peer_buffers || !state) return fail(BBB_E_INVALID, "NULL pointer");
     if (S_local < 0 || S_total <= 0 || B <= 0 || C <= 0) return fail(BBB_E_INVALID, "bad S/B/C");
     if (S_local > 0 && !logits) return fail(BBB_E_INVALID, "S_local > 0 but logits is NULL");
@@ -381,12 +391,14 @@ int bbb_mc_exchange(const float* logits, int32_t S_local, int32_t S_total, int32
     if ((pred || epistemic || aleatoric || entropy) && !(flags & BBB_MC_MOMENTS))
         return fail(BBB_E_INVALID, "uncertainty outputs need BBB_MC_MOMENTS");
     bbb::McxArgs a;
-    a.logits = logits; a.kl = kl; a.S_local = S_local; a.S_total = S_total; a.B = B; a.C = C;
+    a.logits = logits; a.kl = kl; a.n_kl = kl ? (n_kl > 0 ? n_kl : 1) : 0; a.S_local = S_local; a.S_total = S_total; a.B = B; a.C = C;
     a.want_moments = (flags & BBB_MC_MOMENTS) ? 1 : 0; a.normalized = (flags & BBB_MC_NORMALIZED) ? 1 : 0;
     a.labels = (const long long*)labels; a.train_size = train_size; a.beta = beta; a.rank = rank; a.world = world;
     for (int q = 0; q < bbb::MCX_MAX_RANKS; ++q) a.peer[q] = q < world ? (unsigned char*)peer_buffers[q] : nullptr;
     for (int q = 0; q < world; ++q) if (!a.peer[q]) return fail(BBB_E_INVALID, "peer buffer %d is NULL", q);
     a.seq = (unsigned int*)state; a.done = (unsigned int*)state + 1; a.timeouts = (unsigned int*)state + 2;
+    a.noise_base = nullptr; a.noise_inc = 0;
+    if (noise_base) { a.noise_base = (unsigned long long*)noise_base; a.noise_inc = noise_inc; }
     a.timeout_ns = 10ull * 1000 * 1000 * 1000;
     if (const char* e = getenv("BBB_B200_MC_TIMEOUT_MS")) a.timeout_ns = (unsigned long long)atoll(e) * 1000000ull;
     a.head_partials = (double*)((char*)state + 64);

@@ -71,6 +71,21 @@ __device__ __forceinline__ NoiseKey effective_key(NoiseKey k, const unsigned lon
     return k;
 }
 
+// Monte-Carlo samples folded into the batch (LRT: samples differ only in their per-activation noise, so S samples of a
+// batch are one launch over S*rows rows): row b of the folded batch is image b % rows of sample b / rows, drawn from the
+// stream of that sample = stream + (b / rows) * stride -- bit-identical to S separate launches.
+struct McFold { int rows; unsigned long long stride; };
+__device__ __forceinline__ NoiseKey fold_key(NoiseKey k, const McFold& f, int b, int& b_in_sample) {
+    b_in_sample = b;
+    if (f.rows > 0) {
+        const int j = b / f.rows;
+        b_in_sample = b - j * f.rows;
+        const unsigned long long s = (((unsigned long long)k.stream_hi << 32) | k.stream_lo) + (unsigned long long)j * f.stride;
+        k.stream_lo = (uint32_t)s; k.stream_hi = (uint32_t)(s >> 32);
+    }
+    return k;
+}
+
 // four normals of group g (elements 4g .. 4g+3)
 __device__ __forceinline__ float4 normal4(uint64_t grp, const NoiseKey& k) {
     const uint4 r = philox4x32_10(make_uint4((uint32_t)grp, (uint32_t)(grp >> 32), k.stream_lo, k.stream_hi),

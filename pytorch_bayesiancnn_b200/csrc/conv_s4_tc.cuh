@@ -42,6 +42,7 @@ struct S4Args {
     __nv_bfloat16* wtiles; float* bias_ws;
     int planes, out_pitch;
     int lpad, wp, rows;            // left zero pad in pixels (PW + 1), staged row width in pixels, staged rows per image (4 + KH)
+    McFold fold;                   // MC samples folded into the batch (rows = 0: off); x then holds fold.rows images
     long long* trace; long long* tl_prep; long long* tl_gemm;
 };
 
@@ -190,12 +191,13 @@ conv_s4_kernel(const S4Args p) {
         // loop counter) -- straight-line code executed once per CTA, which is what the cold instruction cache punishes.
         const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(half * 32);
         const uint32_t noise_col = 256u;
-        const NoiseKey nkey = effective_key(p.key, p.stream_base);
+        int b_s = b;                                                        // image index inside its MC sample
+        const NoiseKey nkey = fold_key(effective_key(p.key, p.stream_base), p.fold, b, b_s);
         auto noise_slice = [&](int it) {                                    // 16 of this thread's 64 normals: 4 independent Philox chains
             const int ohl = it >> 1, k16 = it & 1;
             float z[16];
             if (bvalid) {
-                const uint64_t g0 = (((uint64_t)b * g.OHW + (uint64_t)((2 * ohp + ohl) * g.OW + ow)) * g.N + half * 32 + k16 * 16) >> 2;
+                const uint64_t g0 = (((uint64_t)b_s * g.OHW + (uint64_t)((2 * ohp + ohl) * g.OW + ow)) * g.N + half * 32 + k16 * 16) >> 2;
                 const float4 za = normal4(g0, nkey), zb = normal4(g0 + 1, nkey), zc = normal4(g0 + 2, nkey), zd = normal4(g0 + 3, nkey);
                 z[0] = za.x; z[1] = za.y; z[2] = za.z; z[3] = za.w; z[4] = zb.x; z[5] = zb.y; z[6] = zb.z; z[7] = zb.w;
                 z[8] = zc.x; z[9] = zc.y; z[10] = zc.z; z[11] = zc.w; z[12] = zd.x; z[13] = zd.y; z[14] = zd.z; z[15] = zd.w;
@@ -222,6 +224,7 @@ conv_s4_kernel(const S4Args p) {
             *sptr(imgx + off) = z4;
             if (two) *sptr(imgx2 + off) = z4;
         }
+        if (tr && threadIdx.x == 0) tr[40] = clock64();
         // thread -> (float4 group gq, row slot rs); it walks the staged rows rs, rs + rstep, ... (no divisions in the loop)
         const int gq = t % groups, rs = t / groups, rstep = 256 / groups;
         const size_t chw = (size_t)g.Cin * g.HW;
@@ -238,7 +241,7 @@ conv_s4_kernel(const S4Args p) {
                 c[u][0] = c[u][1] = c[u][2] = c[u][3] = make_float4(0.f, 0.f, 0.f, 0.f);
                 off[u] = rowi < n_rows ? (uint32_t)rowi * rowb + (uint32_t)(p.lpad + gq * 4) * 8u : 0xffffffffu;   // 16-byte aligned: lpad even
                 if (rowi < n_rows && bb < g.B && (unsigned)ih < (unsigned)g.H) {
-                    const float* src = p.x + (size_t)bb * chw + (size_t)ih * g.W + gq * 4;
+                    const float* src = p.x + (size_t)(p.fold.rows > 0 ? bb % p.fold.rows : bb) * chw + (size_t)ih * g.W + gq * 4;
                     c[u][0] = __ldg(reinterpret_cast<const float4*>(src));
                     if (g.Cin > 1) c[u][1] = __ldg(reinterpret_cast<const float4*>(src + g.HW));
                     if (g.Cin > 2) c[u][2] = __ldg(reinterpret_cast<const float4*>(src + 2 * g.HW));
@@ -247,7 +250,9 @@ conv_s4_kernel(const S4Args p) {
                 rowi += rstep; lr += rstep;
                 while (lr >= p.rows) { lr -= p.rows; ++im; }
             }
-            if (philox && nit < 4) { noise_slice(nit); ++nit; }             // Philox math while the loads are in flight
+            if (tr && threadIdx.x == 0) tr[41 + 3 * nit] = clock64();
+            if (philox && nit < 4) { noise_slice(nit); }                    // Philox math while the loads are in flight
+            if (tr && threadIdx.x == 0) tr[42 + 3 * nit] = clock64();
 #pragma unroll
             for (int u = 0; u < SB; ++u) {
                 if (off[u] == 0xffffffffu) continue;
@@ -261,6 +266,8 @@ conv_s4_kernel(const S4Args p) {
                     *sptr(imgx2 + off[u] + 16u) = make_uint4(bf16x2_sq(bq.x), bf16x2_sq(bq.y), bf16x2_sq(bq.z), bf16x2_sq(bq.w));
                 }
             }
+            if (tr && threadIdx.x == 0) tr[43 + 3 * nit] = clock64();
+            ++nit;
         }
         fence_proxy_async();                                                // generic-proxy stores -> visible to the tensor core
         mbar_arrive(smem_u32(&ctl->img_ready));

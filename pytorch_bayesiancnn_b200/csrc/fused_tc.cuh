@@ -44,6 +44,7 @@ struct FusedArgs {
     long long* trace;            // debug: per-CTA clock64 checkpoints (nullptr in production)
     long long* tl_prep; long long* tl_gemm;   // debug: timeline slots of the two launches (nullptr in production)
     int units;                   // K blocks per pipeline step (TAP_UNITS, or 1 in the two-CTAs-per-SM LRT configuration)
+    McFold fold;                 // MC samples folded into the batch (rows = 0: off)
 };
 
 __host__ __device__ inline size_t fused_wtile_elems(const FusedArgs& a) { return (size_t)a.planes * a.ng * 64; }
@@ -493,7 +494,8 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
         const int n_base = p.pool ? cb * 16 + h * 8 : cb * 64 + h * 32;          // first output channel of chunk 0
         // (1) while the main loop runs: draw this row's LRT noise and park it in tensor memory
         if (philox) {
-            const NoiseKey nkey = effective_key(p.key, p.stream_base);
+            int b_s = b;                                 // image index inside its MC sample
+            const NoiseKey nkey = fold_key(effective_key(p.key, p.stream_base), p.fold, b, b_s);
 #pragma unroll 1
             for (int k = 0; k < 4; ++k) {
                 int oh, ow;
@@ -503,7 +505,7 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
                     float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (bvalid && n0 + 4 * hh < g.N) z = act_noise4(nkey, b, oh * g.OW + ow, n0 + 4 * hh, g.OHW, g.N);
+                    if (bvalid && n0 + 4 * hh < g.N) z = act_noise4(nkey, b_s, oh * g.OW + ow, n0 + 4 * hh, g.OHW, g.N);
                     z8[4 * hh] = z.x; z8[4 * hh + 1] = z.y; z8[4 * hh + 2] = z.z; z8[4 * hh + 3] = z.w;
                 }
                 tmem_st8(lane_base + TAP_NOISE_COL + (uint32_t)(p.pool ? k * 16 + h * 8 : h * 32 + k * 8), z8);

@@ -28,7 +28,9 @@ constexpr int MCX_MAX_RANKS = 16, MCX_MAX_CTAS = 64, MCX_CTRL_BYTES = 4096, MCX_
 
 struct McxArgs {
     const float* logits;          // [S_local, B, C] this rank's samples
-    const float* kl;              // device scalar: the KL of ONE sample (identical for every sample); nullable
+    const float* kl;              // n_kl device floats whose SUM is the KL of ONE sample (e.g. the per-layer terms; identical for
+    int n_kl;                     // every sample); nullable
+    unsigned long long* noise_base; unsigned long long noise_inc;   // optional: *noise_base += noise_inc when the launch is done
     int S_local, S_total, B, C;
     int want_moments, normalized; // moments: also exchange sum p, sum p^2, sum logits;  normalized: p_hat = softplus/sum softplus
     const long long* labels;      // [B] int64, nullable
@@ -122,7 +124,9 @@ mc_exchange_kernel(const McxArgs p) {
     }
     if (blockIdx.x == 0 && threadIdx.x < p.world) {             // this rank's KL contribution: S_local * kl
         float* dst = reinterpret_cast<float*>(p.peer[threadIdx.x] + MCX_CTRL_BYTES) + slot_off + (size_t)p.rank * rank_floats;
-        dst[(size_t)mcx_planes(p.want_moments) * BC] = p.kl ? (float)p.S_local * __ldg(p.kl) : 0.0f;
+        float one = 0.0f;
+        for (int i = 0; p.kl && i < p.n_kl; ++i) one += __ldg(p.kl + i);
+        dst[(size_t)mcx_planes(p.want_moments) * BC] = (float)p.S_local * one;
     }
     __syncthreads();
     // ---- (2) publish: everything this CTA stored is visible system-wide before the flag is ----------------
@@ -208,6 +212,7 @@ mc_exchange_kernel(const McxArgs p) {
                 p.head[2] = (float)(hit / (double)B);                     // metrics.py:23-24
                 p.head[3] = p.beta * kl;
             }
+            if (p.noise_base) *p.noise_base += p.noise_inc;               // the next step's kernels draw fresh Philox streams
             *p.done = 0u;
             *p.seq = seq;
         }

@@ -43,8 +43,9 @@ def _is_pool22(m):
             and m.dilation in (1, (1, 1)) and not m.ceil_mode and not m.return_indices)
 
 
-def plan(children, x_shape):
-    """Return the list of fused steps for this child list and input shape, or None."""
+def plan(children, x_shape, fold=None):
+    """Return the list of fused steps for this child list and input shape, or None.
+    ``fold`` = (rows per MC sample, Philox stream stride): x_shape[0] is then the FOLDED batch (samples x rows)."""
     from .modules import _BayesLayer, FlattenLayer
     if len(x_shape) != 4:
         return None
@@ -116,7 +117,7 @@ def plan(children, x_shape):
     # discover an unsupported shape after noise was drawn and prep kernels were enqueued on side streams
     lib = L.lib()
     for st in steps:
-        d = _step_desc(st, 0)
+        d = _step_desc(st, 0, fold)
         rc = lib.bbb_fused_supported(C.byref(d), st.in_layout, _in_pitch(st), st.prev_hw, st.out_layout, _out_pitch(st))
         if rc == -2:                            # BBB_E_UNSUPPORTED: not fusable, the caller runs child by child
             return None
@@ -134,7 +135,7 @@ def _out_pitch(st):
     return cout * oh * ow if st.out_layout == L.LAYOUT_PACKED_BF16 else 0
 
 
-def _step_desc(st, phase):
+def _step_desc(st, phase, fold=None):
     m = st.layer
     cin, h, w = st.in_shape
     d = L.LayerDesc()
@@ -153,11 +154,37 @@ def _step_desc(st, phase):
     d.epilogue_act = st.act
     d.pool_k = d.pool_s = 2 if st.pool else 0
     d.reserved[0] = phase
+    if fold is not None:                    # MC samples folded into the batch (include/bbb_b200.h)
+        rows, stride = fold
+        d.reserved[1] = int(rows)
+        d.reserved[2] = C.c_int32(stride & 0xFFFFFFFF).value
+        d.reserved[3] = C.c_int32((stride >> 32) & 0xFFFFFFFF).value
     d.prior_mu, d.prior_sigma = float(m.prior_mu), float(m.prior_sigma)
     return d
 
 
 _side_streams: dict = {}
+_direct = {"out": None, "terms": False}
+
+
+class direct_output:
+    """``with fused.direct_output(buf): logits, kls = net(x)`` -- a fused chain entered inside writes its final fp32
+    logits straight into ``buf`` ([B, C], contiguous) and returns the per-layer KL scalars UN-summed (the caller's
+    kernel sums them: bbb_mc_exchange), so the Monte-Carlo step has no copy and no aten reduction behind the chain.
+    ``.used`` tells whether a fused chain really took the buffer (non-fusable nets ignore the hook)."""
+
+    def __init__(self, out):
+        self.out, self.used = out, False
+
+    def __enter__(self):
+        self.prev = dict(_direct)
+        _direct.update(out=self.out, terms=True, owner=self)
+        return self
+
+    def __exit__(self, *exc):
+        _direct.clear()
+        _direct.update(self.prev)
+        return False
 
 
 def _side_stream(dev, i=0):
@@ -172,6 +199,10 @@ def _prep_chains():
 
 
 def run(steps, x: torch.Tensor, overlap_prep: bool = True):
+    return _run(steps, x, overlap_prep, _direct.get("out"), _direct.get("terms", False), _direct.get("owner"))
+
+
+def _run(steps, x, overlap_prep, out, terms, owner, fold=None):
     """Execute a planned chain.  Returns (network output fp32, summed KL 0-dim tensor).
 
     The parameter-only half of every layer (softplus / eps / bf16 operand tiles / KL) runs on side
@@ -188,6 +219,8 @@ def run(steps, x: torch.Tensor, overlap_prep: bool = True):
     chains = [_side_stream(dev, c) for c in range(min(_prep_chains(), len(steps)))] if overlap_prep else []
     forked = False
     try:
+        if fold is not None and Fn.external_eps_active():
+            raise L.EngineError("MC-sample folding draws its noise in-kernel (no external eps)")
         noise = [_draw_noise(st, x.shape[0], dev) for st in steps]
         if overlap_prep:
             for side in chains:
@@ -197,24 +230,33 @@ def run(steps, x: torch.Tensor, overlap_prep: bool = True):
             for i, st in enumerate(steps):
                 side = chains[i % len(chains)]
                 with torch.cuda.stream(side):
-                    run_step(st, None, None, None, 0, kl=kls[i], noise=noise[i], phase=L.FUSED_PREP_ONLY)
+                    run_step(st, None, None, None, 0, kl=kls[i], noise=noise[i], phase=L.FUSED_PREP_ONLY, fold=fold)
                     ev = torch.cuda.Event()
                     ev.record(side)
                     events.append(ev)
             for side in chains[1:]:
                 chains[0].wait_stream(side)
-            with torch.cuda.stream(chains[0]):
-                kl_total = kls.sum()
+            if not terms:
+                with torch.cuda.stream(chains[0]):
+                    kl_total = kls.sum()
         cur, cur_sq, cur_pitch = x.contiguous().float(), None, 0
+        last = steps[-1]
+        take = (out is not None and last.out_layout == L.LAYOUT_ROWMAJOR_F32 and out.is_contiguous()
+                and out.dtype == torch.float32 and tuple(out.shape) == (last.batch, last.out_chw[0]))
         for i, st in enumerate(steps):
             nxt = steps[i + 1].layer if i + 1 < len(steps) else None
+            y_into = out if (take and i == len(steps) - 1) else None
             if overlap_prep:
                 main.wait_event(events[i])
                 cur, cur_sq, cur_pitch = run_step(st, nxt, cur, cur_sq, cur_pitch, kl=kls[i], noise=noise[i],
-                                                  phase=L.FUSED_SKIP_PREP)
+                                                  phase=L.FUSED_SKIP_PREP, y_into=y_into, fold=fold)
             else:
-                cur, cur_sq, cur_pitch = run_step(st, nxt, cur, cur_sq, cur_pitch, kl=kls[i], noise=noise[i])
-        if not overlap_prep:
+                cur, cur_sq, cur_pitch = run_step(st, nxt, cur, cur_sq, cur_pitch, kl=kls[i], noise=noise[i], y_into=y_into, fold=fold)
+        if terms:
+            kl_total = kls
+            if owner is not None:
+                owner.used = True
+        elif not overlap_prep:
             kl_total = kls.sum()
     except BaseException:
         Fn.noise_restore(snap)                 # a retry / fallback sees the stream ids and eps queue it would have seen
@@ -247,7 +289,7 @@ def _draw_noise(st, B, dev):
     return eps_a, eps_b, seed, stream_id, base
 
 
-def run_step(st, nxt, cur, cur_sq, cur_pitch, kl=None, noise=None, phase=0):
+def run_step(st, nxt, cur, cur_sq, cur_pitch, kl=None, noise=None, phase=0, y_into=None, fold=None):
     """One fused layer call: (y, y_sq, pitch) = step(cur, cur_sq).  phase: 0 = prep + GEMM,
     FUSED_PREP_ONLY / FUSED_SKIP_PREP = one half (see include/bbb_b200.h)."""
     lib = L.lib()
@@ -256,7 +298,7 @@ def run_step(st, nxt, cur, cur_sq, cur_pitch, kl=None, noise=None, phase=0):
     B = st.batch                                    # (packed inputs carry rows padded to the 128-row tile)
     if True:
         cin, h, w = st.in_shape
-        d = _step_desc(st, phase)
+        d = _step_desc(st, phase, fold)
         in_pitch = cur_pitch if st.in_layout == L.LAYOUT_NCHW_F32 else cin * h * w
         cout, oh, ow = st.out_chw
         if phase == L.FUSED_PREP_ONLY:
@@ -267,7 +309,7 @@ def run_step(st, nxt, cur, cur_sq, cur_pitch, kl=None, noise=None, phase=0):
             y = torch.empty((B + 127) // 128 * 128, pitch * planes, dtype=torch.bfloat16, device=dev)
             y_sq = y.view(-1)[128 * 64:] if planes == 2 else None      # x^2 blocks interleaved behind the x blocks
         elif st.out_layout == L.LAYOUT_ROWMAJOR_F32:
-            pitch, y, y_sq = 0, torch.empty(B, cout, dtype=torch.float32, device=dev), None
+            pitch, y, y_sq = 0, (y_into if y_into is not None else torch.empty(B, cout, dtype=torch.float32, device=dev)), None
         else:
             pitch, y, y_sq = 0, torch.empty(B, cout, oh, ow, dtype=torch.float32, device=dev), None
         if kl is None:

@@ -64,7 +64,7 @@ class MCForward:
     def __init__(self, net, example_x: torch.Tensor, num_ens: int, group=None, want_uncertainty: bool = False,
                  normalized: bool = False, with_labels: bool = False, train_size: float = 1.0, beta: float = 0.0,
                  seed: Optional[int] = None, graph: bool = True, num_classes: Optional[int] = None,
-                 static_inputs=None, first_replay: int = 0):
+                 static_inputs=None, first_replay: int = 0, fold: bool = True):
         """``static_inputs``: device tensors the caller fills in place (e.g. targets of its host->device copies, or a
         rotation of resident batches); one graph is captured per tensor and ``self(slot=k)`` runs the step on
         ``static_inputs[k]`` with no staging copy.  ``first_replay``: index of the first replay's noise block."""
@@ -115,6 +115,19 @@ class MCForward:
             ptrs = self._open_peers(nbytes)
         self.peers = (C.c_void_p * self.world)(*ptrs)
         self.base = torch.zeros(1, dtype=torch.int64, device=dev)
+        # LRT nets: the local samples differ only in their per-activation noise, so they FOLD into the batch -- one pass
+        # of the fused chain over S_local*B rows (what uncertainty_estimation.py:38-41 does by repeating the input), each
+        # row drawing from its own sample's Philox stream; the KL is computed once.  BBB nets (a weight draw per sample)
+        # and nets the chain cannot take run sample by sample.
+        self.fold_steps = None
+        if fold and len(self.ids) > 1:
+            from . import fused
+            from .modules import _BayesLayer
+            kids = list(net.children())
+            layers = [m_ for m_ in kids if isinstance(m_, _BayesLayer)]
+            if layers and all(m_._variant == L.VARIANT_LRT for m_ in layers) and getattr(net, "fuse", True):
+                self.fold = (self.B, self.world << 40)
+                self.fold_steps = fused.plan(kids, (len(self.ids) * self.B,) + tuple(example_x.shape[1:]), self.fold)
         self.graph, self.graphs = None, []
         self.replays = 0
         self.kernels_per_step = None
@@ -161,24 +174,41 @@ class MCForward:
             self._imported, self._own = [], None
 
     # -- one step ----------------------------------------------------------------------------------------------
-    def _step(self, x, base=None):
+    def _step(self, x, base=None, advance=False):
+        """This rank's samples through the engine, then the exchange kernel.  A fused chain writes its logits straight
+        into the sample buffer and hands over its per-layer KL scalars un-summed (fused.direct_output); with
+        ``advance`` the exchange kernel also moves the Philox stream base for the next replay."""
+        from . import fused
+        from .graph import _STRIDE
         with torch.no_grad():
-            for k, j in enumerate(self.ids):
-                with Fn.stream_base(base), Fn.mc_sample(j, self.seed):
+            kl_ptr, n_kl = None, 0
+            if self.fold_steps is not None:
+                with Fn.stream_base(base), Fn.mc_sample(self.ids[0], self.seed):
+                    _, kls = fused._run(self.fold_steps, x, True, self.logits.view(len(self.ids) * self.B, self.C), True, None,
+                                        fold=self.fold)
+                self._kl_terms = kls
+                kl_ptr, n_kl = Fn._ptr(kls), kls.numel()
+            for k, j in enumerate(self.ids if self.fold_steps is None else ()):
+                with Fn.stream_base(base), Fn.mc_sample(j, self.seed), fused.direct_output(self.logits[k]) as hook:
                     logits, kl = self.net(x)
-                self.logits[k].copy_(logits.reshape(self.B, self.C))
+                if not hook.used:
+                    self.logits[k].copy_(logits.reshape(self.B, self.C))
                 if k == 0:
-                    self.kl_one.copy_(torch.as_tensor(kl, dtype=torch.float32, device=self.dev))
+                    if hook.used:
+                        self._kl_terms = kl                       # per-layer scalars of sample 0 (every sample has the same KL)
+                        kl_ptr, n_kl = Fn._ptr(kl), kl.numel()
+                    else:
+                        self.kl_one.copy_(torch.as_tensor(kl, dtype=torch.float32, device=self.dev))
+                        kl_ptr, n_kl = Fn._ptr(self.kl_one), 1
             if not self.ids and self.rank == 0:
                 raise L.EngineError("MCForward: rank 0 must own a sample")
             o = self.out
             rc = L.lib().bbb_mc_exchange(
-                Fn._ptr(self.logits), len(self.ids), self.num_ens, self.B, self.C,
-                Fn._ptr(self.kl_one) if self.ids else None, self.flags, Fn._ptr(self.labels),
-                C.c_float(self.train_size), C.c_float(self.beta), self.rank, self.world, self.peers,
+                Fn._ptr(self.logits), len(self.ids), self.num_ens, self.B, self.C, kl_ptr, n_kl, self.flags,
+                Fn._ptr(self.labels), C.c_float(self.train_size), C.c_float(self.beta), self.rank, self.world, self.peers,
                 Fn._ptr(self.state), Fn._ptr(o["log_outputs"]), Fn._ptr(o["kl"]), Fn._ptr(o.get("pred")),
                 Fn._ptr(o.get("epistemic")), Fn._ptr(o.get("aleatoric")), Fn._ptr(o.get("entropy")), Fn._ptr(o.get("head")),
-                Fn._stream(self.dev))
+                Fn._ptr(base) if advance else None, C.c_uint64(_STRIDE if advance else 0), Fn._stream(self.dev))
             L.check(rc, "bbb_mc_exchange")
         return self.out
 
@@ -196,12 +226,11 @@ class MCForward:
             g = torch.cuda.CUDAGraph()
             n0 = L.launch_count()
             with torch.cuda.graph(g):
-                Fn.noise_advance(self.base, _STRIDE)
-                self._step(xin, self.base)
+                self._step(xin, self.base, advance=True)           # the exchange kernel moves the noise base at the end of a step
             self.kernels_per_step = L.launch_count() - n0          # engine kernels captured in one step
             self.graphs.append(g)
         self.graph = self.graphs[0]
-        self.base.fill_((self.first_replay - 1) * _STRIDE)
+        self.base.fill_(self.first_replay * _STRIDE)
 
     def __call__(self, x: Optional[torch.Tensor] = None, labels: Optional[torch.Tensor] = None, slot: int = 0):
         if labels is not None:

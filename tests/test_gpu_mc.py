@@ -53,10 +53,10 @@ def _exchange(dev, logits_per_rank, S_total, labels=None, moments=True, normaliz
                  "head": torch.full((4,), float("nan"), **f32)}
             with torch.cuda.stream(streams[r]):
                 rc = lib.bbb_mc_exchange(
-                    Fn._ptr(lg), 0 if lg is None else lg.shape[0], S_total, B, Cc, Fn._ptr(klt), flags, Fn._ptr(lab),
+                    Fn._ptr(lg), 0 if lg is None else lg.shape[0], S_total, B, Cc, Fn._ptr(klt), 1, flags, Fn._ptr(lab),
                     C.c_float(train_size), C.c_float(beta), r, world, peers, Fn._ptr(states[r]), Fn._ptr(o["lo"]),
                     Fn._ptr(o["kl"]), *(Fn._ptr(o[k]) if moments else None for k in ("pred", "epi", "ale", "ent")),
-                    Fn._ptr(o["head"]) if lab is not None else None, Fn._stream(dev))
+                    Fn._ptr(o["head"]) if lab is not None else None, None, 0, Fn._stream(dev))
                 L.check(rc, "bbb_mc_exchange")
             outs.append(o)
         torch.cuda.synchronize()
@@ -271,7 +271,7 @@ def test_mc_forward_product_path_single_gpu(dev):
     # replay r draws streams base_r + sample namespace: reproduce replay 1 (the second) sample by sample, eagerly
     from pytorch_bayesiancnn_b200.graph import _STRIDE
     logits = []
-    base = torch.full((1,), _STRIDE, dtype=torch.int64, device=dev)         # replay 0 ran at base 0, replay 1 at base 2^20
+    base = torch.full((1,), _STRIDE, dtype=torch.int64, device=dev)         # replay 0 ran at base 0, replay 1 at base 2^20 (moved by the exchange kernel)
     for j in range(4):
         with Fn.stream_base(base), Fn.mc_sample(j, 31), torch.no_grad():
             lg, kl = net(x)
@@ -282,6 +282,23 @@ def test_mc_forward_product_path_single_gpu(dev):
     nll = float(torch.nn.functional.nll_loss(ref, labels.cpu()))
     assert abs(float(out["head"][0]) - (nll * 100.0 + 0.5 * float(kl))) < 1e-3 * abs(nll * 100.0 + 0.5 * float(kl))
     assert eng.timeouts() == 0 and eng.kernels_per_step is not None
+
+
+def test_mc_sample_folding_equals_sample_loop(dev):
+    """LRT: S local samples folded into ONE pass of the fused chain (each row drawing from its own sample's Philox
+    stream) == S passes, one per sample -- same logits, same combine (what makes C3/C4-style steps 2x faster)."""
+    from pytorch_bayesiancnn_b200 import mc
+    net, _ = _net("alexnet", 10, 3, "lrt", dev, "auto")
+    x = torch.randn(200, 3, 32, 32, device=dev)                              # not a multiple of the 128-row tile: samples share tiles
+    a = mc.MCForward(net, x, 5, want_uncertainty=True, seed=11, fold=True)
+    b = mc.MCForward(net, x, 5, want_uncertainty=True, seed=11, fold=False)
+    assert a.fold_steps is not None and b.fold_steps is None
+    oa, ob = a(x), b(x)
+    torch.cuda.synchronize()
+    assert (a.logits - b.logits).abs().max() <= 1e-6 * b.logits.abs().max()
+    for k in ("log_outputs", "kl", "pred", "epistemic", "aleatoric", "entropy"):
+        assert (oa[k] - ob[k]).abs().max() <= 1e-5 * max(1.0, float(ob[k].abs().max())), k
+    assert a.kernels_per_step < b.kernels_per_step
 
 
 # --------------------------------------------------------------------------- #

@@ -28,6 +28,7 @@ with torch.no_grad():
     one = rel[0]
     print("CTA0 full[r] passed:", [int(one[8 + r]) for r in range(11)])
     print("CTA0 row r issued  :", [int(one[24 + r]) for r in range(11)])
+    print("staging checkpoints (mean): zero-fill done, then per batch [loads issued, noise slice done, stored]:", [int(rel[:, 40 + k].mean()) for k in range(7)])
     t0 = t[:, 0].min()
     print("CTA entry spread (cycles):", int((t[:, 0] - t0).double().mean()), int((t[:, 0] - t0).max()), " last exit:", int((t[:, 7] - t0).max()))
 fn(None)
