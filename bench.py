@@ -346,6 +346,26 @@ def run_ours(args):
         if cfg["net"] == "alexnet":
             incumbent = gpu_eager_incumbent(args, dev)
 
+    # ---- sharded TRAINING step (row f1): fwd + bwd + ONE gradient all-reduce + Adam, main_bayesian.py:38-58 semantics ----
+    train = None
+    if args.train_steps > 0 and cfg["net"] == "alexnet":
+        ts = mc.MCTrainStep(net, x_dev[0], S_total, train_size=50000.0, seed=2024)
+        labels = torch.randint(0, C, (B,), device=dev)
+        opt = torch.optim.Adam(net.parameters(), lr=1e-5)
+
+        def tsteps(n):
+            for i in range(n):
+                ts(x_dev[i % n_dev_inputs], labels, 0.1)
+                opt.step()
+
+        window(tsteps, 2)
+        tw = [window(tsteps, args.train_steps) for _ in range(3)]
+        tms = statistics.median(tw) / args.train_steps
+        train = {"value": images_per_step / (tms * 1e-3), "unit": "images/s", "ms_per_step": tms,
+                 "what": "forward (tcgen05 layer kernels) + backward (fp32 CUDA-core wgrad/dgrad, eps regenerated from Philox) + "
+                         "MC exchange/ELBO kernel + one gradient all-reduce + Adam; eager launches (no graph)"}
+        ts.close()
+
     if rank == 0:
         dt = "f32" if args.math == "fp32" else "bf16 operands, f32 accumulate"
         out = {
@@ -378,6 +398,7 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "gpu_eager_incumbent": incumbent,
             "mc_batched": mc_batched,
+            "train": train,
             "exchange_timeouts": timeouts,
             "wall_s_timed_loop": wall,
         }
@@ -611,6 +632,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mc-batch", type=int, default=10, help="also report S MC samples folded into one launch (LRT; 0 = skip)")
+    ap.add_argument("--train-steps", type=int, default=5, help="steps per window of the sharded training-step figure (0 = skip)")
     ap.add_argument("--windows", type=int, default=25, help="timed windows of --steps steps; the median window is reported")
     ap.add_argument("--config", default="headline", choices=list(CONFIGS),
                     help="headline (default: BBBAlexNet-10 B=512, one MC sample per GPU per step) or one of BASELINE.json's configs restated")

@@ -404,6 +404,7 @@ int bbb_mc_exchange(const float* logits, int32_t S_local, int32_t S_total, int32
     a.head_partials = (double*)((char*)state + 64);
     a.log_outputs = log_outputs; a.kl_out = kl_out; a.pred = pred; a.epistemic = epistemic; a.aleatoric = aleatoric;
     a.entropy = entropy; a.head = head;
+    { bbb::Geom tg = {}; tg.M = B; tg.N = C; tg.K = S_local; a.tl = tl_slot(true, "mc_exchange", tg); }
     // the grid depends on B only: CTA c of every rank owns the same images, so flags pair up CTA by CTA.  At most
     // MCX_MAX_CTAS CTAs: all co-resident, so a CTA spinning on a peer's flag never keeps that peer's producer off an SM.
     int grid = (B + bbb::MCX_THREADS / 32 - 1) / (bbb::MCX_THREADS / 32);

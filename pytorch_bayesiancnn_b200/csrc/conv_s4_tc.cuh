@@ -123,7 +123,7 @@ conv_s4_prep_kernel(const S4Args p) {
 
 // ------------------------------------------------------------------ (G) conv
 struct S4Smem {
-    unsigned long long full[S4_STAGES], empty[S4_STAGES], accum, img_ready;
+    unsigned long long full[S4_STAGES], empty[S4_STAGES], accum, img_ready[2];
     uint32_t tmem_base, pad;
     float bias[64], bvar[64];
 };
@@ -161,7 +161,8 @@ conv_s4_kernel(const S4Args p) {
     if (threadIdx.x == 0) {
         for (int s = 0; s < S4_STAGES; ++s) { mbar_init(smem_u32(&ctl->full[s]), 1); mbar_init(smem_u32(&ctl->empty[s]), 1); }
         mbar_init(smem_u32(&ctl->accum), 1);
-        mbar_init(smem_u32(&ctl->img_ready), 256);
+        mbar_init(smem_u32(&ctl->img_ready[0]), 256);
+        mbar_init(smem_u32(&ctl->img_ready[1]), 256);
         fence_barrier_init();
     }
     const uint32_t tmem_cols = (two && !p.eps_a) ? 512u : (two ? 256u : 128u);      // accumulators (+ the LRT noise tile)
@@ -225,56 +226,66 @@ conv_s4_kernel(const S4Args p) {
             if (two) *sptr(imgx2 + off) = z4;
         }
         if (tr && threadIdx.x == 0) tr[40] = clock64();
-        // thread -> (float4 group gq, row slot rs); it walks the staged rows rs, rs + rstep, ... (no divisions in the loop)
+        // Two batches: staged rows [0, split) first -- they are all the first kernel rows need (kernel row r reads staged
+        // rows r and r + 4), so the tensor core starts on rows r < split - 4 while the second batch is still in flight.
+        // thread -> (float4 group gq, slot rs); inside a batch it walks (image, row) pairs rs, rs + rstep, ... image-major
+        // (consecutive slots = consecutive rows of one image = contiguous global memory; no divisions in the loop)
         const int gq = t % groups, rs = t / groups, rstep = 256 / groups;
         const size_t chw = (size_t)g.Cin * g.HW;
-        constexpr int SB = 4;                                               // rows in flight per thread: 12 independent 16-byte loads
-        int rowi = rs, im = rs / p.rows, lr = rs - im * p.rows;
-        int nit = 0;
+        const int split = min(p.rows, 2 * g.SH);
+        constexpr int SB = 4;                                               // (image, row) pairs in flight per thread: 12 independent 16-byte loads
+        int nit = 0, nslice = 0;
 #pragma unroll 1
-        for (; rowi < n_rows; ) {
-            float4 c[SB][4];
-            uint32_t off[SB];
+        for (int batch = 0; batch < 2; ++batch) {
+            const int lr0 = batch ? split : 0, nb = batch ? p.rows - split : split;   // rows of this batch
+            const int n_pairs = S4_IMGS * nb;
+            int pr = rs, im = nb > 0 ? rs / nb : 0, lrb = rs - im * nb;
+#pragma unroll 1
+            for (; pr < n_pairs; ) {
+                float4 c[SB][4];
+                uint32_t off[SB];
 #pragma unroll
-            for (int u = 0; u < SB; ++u) {
-                const int ih = row0 + lr, bb = img0 + im;
-                c[u][0] = c[u][1] = c[u][2] = c[u][3] = make_float4(0.f, 0.f, 0.f, 0.f);
-                off[u] = rowi < n_rows ? (uint32_t)rowi * rowb + (uint32_t)(p.lpad + gq * 4) * 8u : 0xffffffffu;   // 16-byte aligned: lpad even
-                if (rowi < n_rows && bb < g.B && (unsigned)ih < (unsigned)g.H) {
-                    const float* src = p.x + (size_t)(p.fold.rows > 0 ? bb % p.fold.rows : bb) * chw + (size_t)ih * g.W + gq * 4;
-                    c[u][0] = __ldg(reinterpret_cast<const float4*>(src));
-                    if (g.Cin > 1) c[u][1] = __ldg(reinterpret_cast<const float4*>(src + g.HW));
-                    if (g.Cin > 2) c[u][2] = __ldg(reinterpret_cast<const float4*>(src + 2 * g.HW));
-                    if (g.Cin > 3) c[u][3] = __ldg(reinterpret_cast<const float4*>(src + 3 * g.HW));
+                for (int u = 0; u < SB; ++u) {
+                    const int lr = lr0 + lrb, ih = row0 + lr, bb = img0 + im;
+                    c[u][0] = c[u][1] = c[u][2] = c[u][3] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    off[u] = pr < n_pairs ? (uint32_t)(im * p.rows + lr) * rowb + (uint32_t)(p.lpad + gq * 4) * 8u : 0xffffffffu;   // 16-byte aligned: lpad even
+                    if (pr < n_pairs && bb < g.B && (unsigned)ih < (unsigned)g.H) {
+                        const float* src = p.x + (size_t)(p.fold.rows > 0 ? bb % p.fold.rows : bb) * chw + (size_t)ih * g.W + gq * 4;
+                        c[u][0] = __ldg(reinterpret_cast<const float4*>(src));
+                        if (g.Cin > 1) c[u][1] = __ldg(reinterpret_cast<const float4*>(src + g.HW));
+                        if (g.Cin > 2) c[u][2] = __ldg(reinterpret_cast<const float4*>(src + 2 * g.HW));
+                        if (g.Cin > 3) c[u][3] = __ldg(reinterpret_cast<const float4*>(src + 3 * g.HW));
+                    }
+                    pr += rstep; lrb += rstep;
+                    while (lrb >= nb) { lrb -= nb; ++im; }
                 }
-                rowi += rstep; lr += rstep;
-                while (lr >= p.rows) { lr -= p.rows; ++im; }
-            }
-            if (tr && threadIdx.x == 0) tr[41 + 3 * nit] = clock64();
-            if (philox && nit < 4) { noise_slice(nit); }                    // Philox math while the loads are in flight
-            if (tr && threadIdx.x == 0) tr[42 + 3 * nit] = clock64();
+                if (tr && threadIdx.x == 0 && nit < 2) tr[41 + 3 * nit] = clock64();
+                // Philox math while the SECOND batch's loads are in flight (the first batch is what the tensor core waits for)
+                if (philox && batch == 1 && nslice < 1) { noise_slice(nslice); ++nslice; }
+                if (tr && threadIdx.x == 0 && nit < 2) tr[42 + 3 * nit] = clock64();
 #pragma unroll
-            for (int u = 0; u < SB; ++u) {
-                if (off[u] == 0xffffffffu) continue;
-                const uint4 a = make_uint4(pack_bf16(c[u][0].x, c[u][1].x), pack_bf16(c[u][2].x, c[u][3].x), pack_bf16(c[u][0].y, c[u][1].y), pack_bf16(c[u][2].y, c[u][3].y));
-                const uint4 bq = make_uint4(pack_bf16(c[u][0].z, c[u][1].z), pack_bf16(c[u][2].z, c[u][3].z), pack_bf16(c[u][0].w, c[u][1].w), pack_bf16(c[u][2].w, c[u][3].w));
-                *sptr(imgx + off[u]) = a;
-                *sptr(imgx + off[u] + 16u) = bq;
-                if (two) {
-                    // squares of the bf16-rounded values (what the mean path multiplies), one rounding
-                    *sptr(imgx2 + off[u]) = make_uint4(bf16x2_sq(a.x), bf16x2_sq(a.y), bf16x2_sq(a.z), bf16x2_sq(a.w));
-                    *sptr(imgx2 + off[u] + 16u) = make_uint4(bf16x2_sq(bq.x), bf16x2_sq(bq.y), bf16x2_sq(bq.z), bf16x2_sq(bq.w));
+                for (int u = 0; u < SB; ++u) {
+                    if (off[u] == 0xffffffffu) continue;
+                    const uint4 a = make_uint4(pack_bf16(c[u][0].x, c[u][1].x), pack_bf16(c[u][2].x, c[u][3].x), pack_bf16(c[u][0].y, c[u][1].y), pack_bf16(c[u][2].y, c[u][3].y));
+                    const uint4 bq = make_uint4(pack_bf16(c[u][0].z, c[u][1].z), pack_bf16(c[u][2].z, c[u][3].z), pack_bf16(c[u][0].w, c[u][1].w), pack_bf16(c[u][2].w, c[u][3].w));
+                    *sptr(imgx + off[u]) = a;
+                    *sptr(imgx + off[u] + 16u) = bq;
+                    if (two) {
+                        // squares of the bf16-rounded values (what the mean path multiplies), one rounding
+                        *sptr(imgx2 + off[u]) = make_uint4(bf16x2_sq(a.x), bf16x2_sq(a.y), bf16x2_sq(a.z), bf16x2_sq(a.w));
+                        *sptr(imgx2 + off[u] + 16u) = make_uint4(bf16x2_sq(bq.x), bf16x2_sq(bq.y), bf16x2_sq(bq.z), bf16x2_sq(bq.w));
+                    }
                 }
+                if (tr && threadIdx.x == 0 && nit < 2) tr[43 + 3 * nit] = clock64();
+                ++nit;
             }
-            if (tr && threadIdx.x == 0) tr[43 + 3 * nit] = clock64();
-            ++nit;
+            fence_proxy_async();                                            // generic-proxy stores -> visible to the tensor core
+            mbar_arrive(smem_u32(&ctl->img_ready[batch]));
         }
-        fence_proxy_async();                                                // generic-proxy stores -> visible to the tensor core
-        mbar_arrive(smem_u32(&ctl->img_ready));
         if (tr && threadIdx.x == 0) tr[2] = clock64();
         if (philox) {
 #pragma unroll 1
-            for (; nit < 4; ++nit) noise_slice(nit);                        // the rest, while the tensor core works
+            for (; nslice < 4; ++nslice) noise_slice(nslice);                        // the rest, while the tensor core works
             tmem_st_wait();
         }
         if (tr && threadIdx.x == 0) tr[3] = clock64();
@@ -288,7 +299,7 @@ conv_s4_kernel(const S4Args p) {
         const bool odd = ow & 1;
         const int pp = ohp * (g.OW >> 1) + (ow >> 1);
         const int kb_total = p.out_pitch >> 6, planes_out = p.y_sq ? 2 : 1;
-#pragma unroll 1
+#pragma unroll 2
         for (int c8 = 0; c8 < 4; ++c8) {                                    // 8 of this thread's 32 columns per iteration
             const int n0 = half * 32 + c8 * 8;
             float best[8];
@@ -351,12 +362,18 @@ conv_s4_kernel(const S4Args p) {
         }
         const uint64_t dB0 = make_smem_desc(ring, 1024u, 128u);
         const uint32_t acc1 = (uint32_t)(p.planes * 64);                     // accumulators of the second output row
+        const int split = min(p.rows, 2 * g.SH);
         __syncwarp();
-        mbar_wait(smem_u32(&ctl->img_ready), 0u);
+        mbar_wait(smem_u32(&ctl->img_ready[0]), 0u);
         tc_fence_after();
 #pragma unroll 1
         for (int r = 0; r < g.KH; ++r) {
             const int s = r % S4_STAGES;
+            if (r + g.SH == split) {                                        // staged row r + 4 belongs to the second batch
+                __syncwarp();
+                mbar_wait(smem_u32(&ctl->img_ready[1]), 0u);
+                tc_fence_after();
+            }
             __syncwarp();                                                   // converged whole-warp wait (single-lane waits wake late)
             mbar_wait(smem_u32(&ctl->full[s]), (uint32_t)(r / S4_STAGES) & 1u);
             tc_fence_after();

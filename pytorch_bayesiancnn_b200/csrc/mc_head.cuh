@@ -47,6 +47,7 @@ struct McxArgs {
     float* kl_out;                // scalar: sum_j kl_j / S_total
     float* pred; float* epistemic; float* aleatoric; float* entropy;   // [B,C] x3, [B]; nullable (need want_moments)
     float* head;                  // [4]: loss, nll, accuracy, beta*kl; nullable (needs labels)
+    long long* tl;                // debug timeline slot (nullptr in production)
 };
 
 __host__ __device__ inline int mcx_planes(int want_moments) { return want_moments ? 5 : 2; }
@@ -74,6 +75,7 @@ mc_exchange_kernel(const McxArgs p) {
     const int B = p.B, C = p.C, BC = B * C;
     const int rows_per_cta = (B + gridDim.x - 1) / gridDim.x;
     const int b0 = blockIdx.x * rows_per_cta, b1 = min(B, b0 + rows_per_cta);
+    tl_enter(p.tl);
     if (threadIdx.x == 0) seq_sh = *p.seq + 1u;
     __syncthreads();
     const unsigned int seq = seq_sh;
@@ -217,6 +219,7 @@ mc_exchange_kernel(const McxArgs p) {
             *p.seq = seq;
         }
     }
+    tl_exit(p.tl);
 }
 
 }  // namespace bbb

@@ -90,7 +90,7 @@ def begin_sample(sample_id: int):
 
 
 @contextlib.contextmanager
-def mc_sample(sample_id: int, seed: Optional[int] = None):
+def mc_sample(sample_id: int, seed: Optional[int] = None, offset: int = 0):
     """Layer calls inside draw Monte-Carlo evaluation sample `sample_id` (global id): stream ids
     2^63 + (sample_id << 40) + 0, 1, 2, ... (2^40 ids per sample: room for 2^20 CUDA-graph replays of 2^20 layer calls)
     -- a namespace training never reaches, independent of how the samples are sharded over ranks.  The thread's training counter (and seed) are restored on exit, so an evaluation pass
@@ -99,7 +99,7 @@ def mc_sample(sample_id: int, seed: Optional[int] = None):
     saved = (_noise.seed, _noise.counter, _noise.explicit)
     if seed is not None:
         _noise.seed, _noise.explicit = int(seed) & _MASK64, True
-    _noise.counter = _MC_NAMESPACE | (int(sample_id) << 40)
+    _noise.counter = (_MC_NAMESPACE | (int(sample_id) << 40)) + int(offset)     # offset: e.g. training step * 2^20
     try:
         yield
     finally:

@@ -179,7 +179,6 @@ class MCForward:
         into the sample buffer and hands over its per-layer KL scalars un-summed (fused.direct_output); with
         ``advance`` the exchange kernel also moves the Philox stream base for the next replay."""
         from . import fused
-        from .graph import _STRIDE
         with torch.no_grad():
             kl_ptr, n_kl = None, 0
             if self.fold_steps is not None:
@@ -202,15 +201,20 @@ class MCForward:
                         kl_ptr, n_kl = Fn._ptr(self.kl_one), 1
             if not self.ids and self.rank == 0:
                 raise L.EngineError("MCForward: rank 0 must own a sample")
-            o = self.out
-            rc = L.lib().bbb_mc_exchange(
-                Fn._ptr(self.logits), len(self.ids), self.num_ens, self.B, self.C, kl_ptr, n_kl, self.flags,
-                Fn._ptr(self.labels), C.c_float(self.train_size), C.c_float(self.beta), self.rank, self.world, self.peers,
-                Fn._ptr(self.state), Fn._ptr(o["log_outputs"]), Fn._ptr(o["kl"]), Fn._ptr(o.get("pred")),
-                Fn._ptr(o.get("epistemic")), Fn._ptr(o.get("aleatoric")), Fn._ptr(o.get("entropy")), Fn._ptr(o.get("head")),
-                Fn._ptr(base) if advance else None, C.c_uint64(_STRIDE if advance else 0), Fn._stream(self.dev))
-            L.check(rc, "bbb_mc_exchange")
+            self._exchange(kl_ptr, n_kl, base if advance else None)
         return self.out
+
+    def _exchange(self, kl_ptr, n_kl, advance_base=None):
+        """The one kernel behind the samples: combine + exchange + heads (bbb_mc_exchange)."""
+        from .graph import _STRIDE
+        o = self.out
+        rc = L.lib().bbb_mc_exchange(
+            Fn._ptr(self.logits), len(self.ids), self.num_ens, self.B, self.C, kl_ptr, n_kl, self.flags,
+            Fn._ptr(self.labels), C.c_float(self.train_size), C.c_float(self.beta), self.rank, self.world, self.peers,
+            Fn._ptr(self.state), Fn._ptr(o["log_outputs"]), Fn._ptr(o["kl"]), Fn._ptr(o.get("pred")),
+            Fn._ptr(o.get("epistemic")), Fn._ptr(o.get("aleatoric")), Fn._ptr(o.get("entropy")), Fn._ptr(o.get("head")),
+            Fn._ptr(advance_base), C.c_uint64(_STRIDE if advance_base is not None else 0), Fn._stream(self.dev))
+        L.check(rc, "bbb_mc_exchange")
 
     def _capture(self, warmup: int = 2):
         from .graph import _STRIDE
@@ -332,3 +336,67 @@ def engine_forward_fn(net) -> Callable:
         with Fn.mc_sample(j), torch.no_grad():
             return net(x)
     return fn
+
+
+class MCTrainStep(MCForward):
+    """One SHARDED training step with main_bayesian.train_model's semantics (main_bayesian.py:38-58): every rank runs
+    its share of the ``num_ens`` weight samples WITH autograd (layer forward kernels + the engine's backward kernels),
+    the exchange kernel combines them into log_outputs / kl / the ELBO (metrics.py:12-14) on every rank, each rank
+    back-propagates d loss / d logits_j of ITS samples -- which needs only the combined log_outputs:
+        d loss / d logits_j[b,:] = -(train_size / B) * softmax_j[b,y_b] / (S * p_bar[b,y_b]) * (onehot(y_b) - softmax_j[b,:])
+    -- plus beta/S of its samples' KL terms, and ONE all-reduce sums the parameter gradients (SURVEY.md 8e "Backward
+    sharding").  The caller owns the optimizer: ``out = step(x, labels, beta); optimizer.step()``.
+
+    Noise: sample j of step t draws Philox streams 2^63 + (j << 40) + t * 2^20 + layer, so R ranks == 1 rank."""
+
+    def __init__(self, net, example_x, num_ens, train_size, group=None, seed=None):
+        super().__init__(net, example_x, num_ens, group=group, with_labels=True, train_size=train_size, seed=seed,
+                         graph=False, fold=False)
+        self.params = [p for p in net.parameters() if p.requires_grad]
+        self.steps = 0
+
+    def __call__(self, x, labels, beta: float = 0.0):
+        from .graph import _STRIDE
+        self.beta = float(beta)
+        self.labels.copy_(labels, non_blocking=True)
+        for p in self.params:
+            p.grad = None
+        logits, kls = [], []
+        for k, j in enumerate(self.ids):
+            with Fn.mc_sample(j, self.seed, offset=self.steps * _STRIDE):
+                lg, kl = self.net(x)                                   # autograd on: per-layer kernels (no fused chain)
+            logits.append(lg)
+            kls.append(kl)
+            self.logits[k].copy_(lg.detach().reshape(self.B, self.C))
+        kl_ptr, n_kl = None, 0
+        if self.ids:
+            self.kl_one.copy_(kls[0].detach())
+            kl_ptr, n_kl = Fn._ptr(self.kl_one), 1
+        self._exchange(kl_ptr, n_kl)
+        o = self.out
+        if self.ids:
+            S = float(self.num_ens)
+            idx = self.labels.view(-1, 1)
+            p_bar_y = o["log_outputs"].gather(1, idx).exp()                 # p_bar[b, y_b]
+            grads = []
+            for lg in logits:
+                sm = torch.softmax(lg.detach().float(), dim=1)
+                w = sm.gather(1, idx) / (S * p_bar_y)
+                onehot = torch.zeros_like(sm).scatter_(1, idx, 1.0)
+                grads.append((-(self.train_size / self.B)) * w * (onehot - sm))
+            kl_g = [torch.full_like(k_, self.beta / S) for k_ in kls if torch.is_tensor(k_) and k_.requires_grad]
+            kl_t = [k_ for k_ in kls if torch.is_tensor(k_) and k_.requires_grad]
+            torch.autograd.backward(logits + kl_t, grads + kl_g)
+        if self.world > 1:                                                  # ONE collective: the summed parameter gradients
+            for p in self.params:
+                if p.grad is None:
+                    p.grad = torch.zeros_like(p)
+            flat = torch.cat([p.grad.reshape(-1) for p in self.params])
+            self.dist.all_reduce(flat, group=self.group)
+            off = 0
+            for p in self.params:
+                n = p.numel()
+                p.grad.copy_(flat[off:off + n].view_as(p))
+                off += n
+        self.steps += 1
+        return o

@@ -301,6 +301,43 @@ def test_mc_sample_folding_equals_sample_loop(dev):
     assert a.kernels_per_step < b.kernels_per_step
 
 
+def _oracle_train_grads(key, params, x, labels, eps_per_sample, variant, classes, train_size, beta):
+    """main_bayesian.py:46-58 through torch autograd on the oracle: grads of every parameter."""
+    from oracle import bbb_oracle as O
+    P = [{k: v.clone().requires_grad_(True) for k, v in p.items()} for p in params]
+    outs, kl = [], 0.0
+    for eps in eps_per_sample:
+        lg, _kl = O.net_forward(key, P, x, eps, variant, "softplus", 0.0, 0.1, classes)
+        outs.append(lg)
+        kl = kl + _kl
+    kl = kl / len(eps_per_sample)
+    log_outputs = O.mc_combine(outs)
+    loss = torch.nn.functional.nll_loss(log_outputs, labels, reduction="mean") * train_size + beta * kl    # metrics.py:12-14
+    loss.backward()
+    return loss.detach(), [p[k].grad for p in P for k in ("W_mu", "W_rho", "bias_mu", "bias_rho")]
+
+
+def test_training_step_matches_oracle_autograd(dev):
+    """Row f1: the sharded training step (one rank here) == main_bayesian.train_model's math on identical noise:
+    loss, and the gradient of every W_mu / W_rho / bias_mu / bias_rho, for 3 MC samples, both variants."""
+    import pytorch_bayesiancnn_b200 as bbb
+    from pytorch_bayesiancnn_b200 import mc
+    for variant in ("lrt", "bbb"):
+        net, params = _net("lenet", 10, 3, variant, dev, "fp32")
+        x = torch.rand(48, 3, 32, 32, generator=torch.Generator().manual_seed(4))
+        labels = torch.randint(0, 10, (48,), generator=torch.Generator().manual_seed(5))
+        step = mc.MCTrainStep(net, x.to(dev), 3, train_size=5000.0, seed=21)
+        out = step(x.to(dev), labels.to(dev), beta=0.1)
+        eps = [_engine_eps(bbb, "lenet", 10, 3, variant, 48, 21, MC_NS | (j << 40), dev) for j in range(3)]
+        ref_loss, ref_grads = _oracle_train_grads("lenet", params, x, labels, eps, variant, 10, 5000.0, 0.1)
+        assert abs(float(out["head"][0]) - float(ref_loss)) <= 1e-4 * abs(float(ref_loss)), (variant, float(out["head"][0]), float(ref_loss))
+        got = [g for m in net.children() if hasattr(m, "W_mu") for g in (m.W_mu.grad, m.W_rho.grad, m.bias_mu.grad, m.bias_rho.grad)]
+        assert len(got) == len(ref_grads)
+        for i, (a, b) in enumerate(zip(got, ref_grads)):
+            e = scale_err(a, b)
+            assert e < 2e-4, (variant, i, e)
+
+
 # --------------------------------------------------------------------------- #
 # real multi-process run: NCCL for the handshake, CUDA-IPC peer buffers for the exchange
 # --------------------------------------------------------------------------- #
@@ -319,8 +356,19 @@ def _mp_worker(rank, world, port, num_ens, out_path):
         out = eng(x, labels)
     torch.cuda.synchronize()
     assert eng.timeouts() == 0
-    torch.save({k: v.cpu() for k, v in out.items()}, out_path + f".{rank}")
+    res = {k: v.cpu() for k, v in out.items()}
     eng.close()
+    # sharded training step (row f1): gradients after ONE all-reduce
+    tnet, _ = _net("lenet", 10, 3, "lrt", dev, "fp32")
+    xt = torch.rand(64, 3, 32, 32, generator=torch.Generator().manual_seed(3)).to(dev)
+    yt = torch.randint(0, 10, (64,), generator=torch.Generator().manual_seed(4)).to(dev)
+    ts = mc.MCTrainStep(tnet, xt, 4, train_size=1000.0, seed=9)
+    tout = ts(xt, yt, beta=0.1)
+    torch.cuda.synchronize()
+    res["train_loss"] = tout["head"].cpu()
+    res["train_grads"] = [p.grad.cpu() for p in tnet.parameters()]
+    ts.close()
+    torch.save(res, out_path + f".{rank}")
     dist.destroy_process_group()
 
 
@@ -344,7 +392,10 @@ def test_mc_forward_multi_gpu_equals_single_gpu(dev, num_ens):
         assert p.exitcode == 0
     outs = [torch.load(out_path + f".{r}") for r in range(world)]
     for k in outs[0]:
-        assert torch.equal(outs[0][k], outs[1][k]), k                      # every rank holds the same result
+        if k == "train_grads":
+            assert all(torch.equal(a, b) for a, b in zip(outs[0][k], outs[1][k]))
+        else:
+            assert torch.equal(outs[0][k], outs[1][k]), k                  # every rank holds the same result
     # single GPU, same global sample seeds, same replay index (the third)
     net, _ = _net("alexnet", 10, 3, "lrt", dev, "auto")
     x = torch.randn(256, 3, 32, 32, generator=torch.Generator().manual_seed(1)).to(dev)
@@ -356,3 +407,13 @@ def test_mc_forward_multi_gpu_equals_single_gpu(dev, num_ens):
     for k in ("log_outputs", "pred", "epistemic", "aleatoric", "entropy", "kl", "head"):
         a, b = one[k].cpu(), outs[0][k]
         assert (a - b).abs().max() <= 1e-4 * max(1.0, float(b.abs().max())), k
+    # the sharded training step: 2 ranks x 2 samples == 1 rank x 4 samples (same global sample streams)
+    tnet, _ = _net("lenet", 10, 3, "lrt", dev, "fp32")
+    xt = torch.rand(64, 3, 32, 32, generator=torch.Generator().manual_seed(3)).to(dev)
+    yt = torch.randint(0, 10, (64,), generator=torch.Generator().manual_seed(4)).to(dev)
+    ts = mc.MCTrainStep(tnet, xt, 4, train_size=1000.0, seed=9)
+    tout = ts(xt, yt, beta=0.1)
+    torch.cuda.synchronize()
+    assert (tout["head"].cpu() - outs[0]["train_loss"]).abs().max() <= 1e-4 * float(outs[0]["train_loss"].abs().max())
+    for p, gref in zip(tnet.parameters(), outs[0]["train_grads"]):
+        assert scale_err(p.grad, gref) < 1e-4

@@ -29,11 +29,22 @@ lib.bbb_debug_timeline_name.argtypes = [C.c_int]
 net = build_net(variant, 10, dev, "bf16")
 xs = [torch.randn(B, 3, 32, 32, device=dev) for _ in range(24)]
 bbb.manual_seed(1)
-bbb.GraphedForward(net, xs[0])                                   # warm-up + plan/workspace creation, untraced
+MC = os.environ.get("TIMELINE_MC", "1") != "0"                  # the public MC step (mc.MCForward) instead of the bare forward
+from pytorch_bayesiancnn_b200 import mc
+if MC:
+    mc.MCForward(net, xs[0], 1, seed=1)                          # warm-up + plan/workspace creation, untraced
+else:
+    bbb.GraphedForward(net, xs[0])
 CAP = 64
 slots = torch.zeros(CAP, 2, dtype=torch.int64, device=dev)
 lib.bbb_debug_set_timeline(C.c_void_p(slots.data_ptr()), CAP)
-g = bbb.GraphedForward(net, xs[0], warmup=0, static_inputs=xs[:1])   # capture only: slot k <-> k-th instrumented launch
+if MC:
+    class _G:                                                    # capture only (the eager warm-up steps inside consume slots too:
+        pass                                                     # the LAST launches belong to the captured graph)
+    eng = mc.MCForward(net, xs[0], 1, seed=1, static_inputs=xs[:1])
+    g = _G(); g.inputs = eng.inputs; g.__class__.__call__ = lambda self: eng()
+else:
+    g = bbb.GraphedForward(net, xs[0], warmup=0, static_inputs=xs[:1])   # capture only: slot k <-> k-th instrumented launch
 n = lib.bbb_debug_timeline_count()
 names = [lib.bbb_debug_timeline_name(k).decode() for k in range(n)]
 lib.bbb_debug_set_timeline(None, 0)
@@ -56,9 +67,10 @@ print(f"BBBAlexNet {variant} B={B}: event-timed replay median {statistics.median
 med = lambda k, j: statistics.median(r[j][k] for r in runs[5:]) / 1e3
 order = sorted(range(n), key=lambda k: med(k, 0))
 print(f"{'kernel':44s} {'start us':>9s} {'end us':>9s} {'dur us':>8s}")
+order = [k for k in order if med(k, 1) > 0 and med(k, 0) < 1e6]     # slots the replay really wrote
 for k in order:
     print(f"{names[k]:44s} {med(k, 0):9.1f} {med(k, 1):9.1f} {med(k, 1) - med(k, 0):8.1f}")
-gemm = [k for k in order if "gemm" in names[k]]
+gemm = [k for k in order if "gemm" in names[k] or "conv_s4 " in names[k]]
 print("GEMM critical path: " + "  ".join(
     f"[{names[k].split()[0]} {med(k, 1) - med(k, 0):.1f}]" + (f" gap {med(gemm[i + 1], 0) - med(k, 1):.1f}" if i + 1 < len(gemm) else "")
     for i, k in enumerate(gemm)))
