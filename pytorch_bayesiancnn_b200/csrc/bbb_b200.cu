@@ -409,8 +409,8 @@ int bbb_mc_exchange(const float* logits, int32_t S_local, int32_t S_total, int32
     // MCX_MAX_CTAS CTAs: all co-resident, so a CTA spinning on a peer's flag never keeps that peer's producer off an SM.
     int grid = (B + bbb::MCX_THREADS / 32 - 1) / (bbb::MCX_THREADS / 32);
     if (grid > bbb::MCX_MAX_CTAS) grid = bbb::MCX_MAX_CTAS;
-    bbb::mc_exchange_kernel<<<grid, bbb::MCX_THREADS, 0, (cudaStream_t)cuda_stream>>>(a);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = bbb::launch_pdl(bbb::mc_exchange_kernel, dim3(grid), dim3(bbb::MCX_THREADS), 0, (cudaStream_t)cuda_stream, a);
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "mc_exchange launch");
     g_launches += 1;
     return BBB_OK;

@@ -76,6 +76,7 @@ mc_exchange_kernel(const McxArgs p) {
     const int rows_per_cta = (B + gridDim.x - 1) / gridDim.x;
     const int b0 = blockIdx.x * rows_per_cta, b1 = min(B, b0 + rows_per_cta);
     tl_enter(p.tl);
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // launched with programmatic serialization: the logits come from the predecessor
     if (threadIdx.x == 0) seq_sh = *p.seq + 1u;
     __syncthreads();
     const unsigned int seq = seq_sh;
@@ -131,23 +132,24 @@ mc_exchange_kernel(const McxArgs p) {
         dst[(size_t)mcx_planes(p.want_moments) * BC] = (float)p.S_local * one;
     }
     __syncthreads();
-    // ---- (2) publish: everything this CTA stored is visible system-wide before the flag is ----------------
-    if (threadIdx.x == 0) __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < p.world) {
-        unsigned int* flags = reinterpret_cast<unsigned int*>(p.peer[threadIdx.x]);
-        st_release_sys(flags + p.rank * MCX_MAX_CTAS + blockIdx.x, seq);
-    }
-    // ---- (3) wait for the same CTA of every peer ---------------------------------------------------------
-    if (threadIdx.x < p.world) {
-        const unsigned int* f = reinterpret_cast<const unsigned int*>(p.peer[p.rank]) + threadIdx.x * MCX_MAX_CTAS + blockIdx.x;
-        const unsigned long long t0 = globaltimer_ns();
-        while ((int)(ld_acquire_sys(f) - seq) < 0) {
-            __nanosleep(20);
-            if (globaltimer_ns() - t0 > p.timeout_ns) { atomicAdd(p.timeouts, 1u); break; }   // never hang the GPU on a lost peer
+    if (p.world > 1) {
+        // ---- (2) publish: everything this CTA stored is visible system-wide before its flags are.  The CTA barrier above
+        // orders the other threads' stores before these threads; each of them then fences at system scope and
+        // releases its flag on one peer.
+        if (threadIdx.x < p.world) {
+            __threadfence_system();
+            unsigned int* flags = reinterpret_cast<unsigned int*>(p.peer[threadIdx.x]);
+            st_release_sys(flags + p.rank * MCX_MAX_CTAS + blockIdx.x, seq);
+            // ---- (3) wait for the same CTA of that peer -------------------------------------------------------
+            const unsigned int* f = reinterpret_cast<const unsigned int*>(p.peer[p.rank]) + threadIdx.x * MCX_MAX_CTAS + blockIdx.x;
+            const unsigned long long t0 = globaltimer_ns();
+            while ((int)(ld_acquire_sys(f) - seq) < 0) {
+                __nanosleep(20);
+                if (globaltimer_ns() - t0 > p.timeout_ns) { atomicAdd(p.timeouts, 1u); break; }   // never hang the GPU on a lost peer
+            }
         }
+        __syncthreads();
     }
-    __syncthreads();
     // ---- (4) finish: fixed rank order => bitwise identical on every rank ----------------------------------
     const float* rx = reinterpret_cast<const float*>(p.peer[p.rank] + MCX_CTRL_BYTES) + slot_off;
     double nll_acc = 0.0, hit_acc = 0.0;

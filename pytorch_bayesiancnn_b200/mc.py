@@ -179,7 +179,10 @@ class MCForward:
         into the sample buffer and hands over its per-layer KL scalars un-summed (fused.direct_output); with
         ``advance`` the exchange kernel also moves the Philox stream base for the next replay."""
         from . import fused
+        import os
         with torch.no_grad():
+            if advance and os.environ.get("BBB_MC_HEAD", "0") == "1":      # experiment: a leading kernel on the capture stream
+                Fn.noise_advance(base, 0)
             kl_ptr, n_kl = None, 0
             if self.fold_steps is not None:
                 with Fn.stream_base(base), Fn.mc_sample(self.ids[0], self.seed):
