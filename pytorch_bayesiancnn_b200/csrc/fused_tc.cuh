@@ -85,13 +85,13 @@ tap_prep_kernel(const FusedArgs p) {
                 const size_t wi = (size_t)n * g.K + (size_t)cin * g.KHW + tap;
                 const float mu = __ldg(p.w_mu + wi);
                 float sigma = 0.0f;
-                if (stoch || do_kl) sigma = softplus_sigma(__ldg(p.w_rho + wi));
+                if (stoch || do_kl) sigma = softplus_sigma_fast(__ldg(p.w_rho + wi));
                 if (LRT) { wv = mu; sv = sigma * sigma; }
                 else if (stoch) {
                     const float e_ = p.eps_a ? __ldg(p.eps_a + wi) : normal1(wi, nkey);
                     wv = mu + e_ * sigma;
                 } else wv = mu;
-                if (do_kl) kl_acc += (double)kl_term(mu, sigma, p.prior_mu, p.prior_sigma, p.kl_convention);
+                if (do_kl) kl_acc += (double)kl_term_fast(mu, sigma, p.prior_mu, p.prior_sigma, p.kl_convention);
             }
             w[e] = wv; s2[e] = sv;
         }
@@ -113,13 +113,13 @@ tap_prep_kernel(const FusedArgs p) {
             float bm = 0.0f, bv = 0.0f;
             if (p.has_bias && n < g.N) {
                 const float mu = __ldg(p.b_mu + n);
-                const float sigma = (stoch || do_kl) ? softplus_sigma(__ldg(p.b_rho + n)) : 0.0f;
+                const float sigma = (stoch || do_kl) ? softplus_sigma_fast(__ldg(p.b_rho + n)) : 0.0f;
                 if (LRT) { bm = mu; bv = sigma * sigma; }
                 else if (stoch) {
                     const float e_ = p.eps_b ? __ldg(p.eps_b + n) : normal1((uint64_t)g.N * g.K + n, nkey);
                     bm = mu + e_ * sigma;
                 } else bm = mu;
-                if (do_kl) kl_acc += (double)kl_term(mu, sigma, p.prior_mu, p.prior_sigma, p.kl_convention);
+                if (do_kl) kl_acc += (double)kl_term_fast(mu, sigma, p.prior_mu, p.prior_sigma, p.kl_convention);
             }
             p.bias_ws[n] = bm;
             p.bias_ws[npad + n] = bv;
@@ -191,13 +191,13 @@ tap_prep_conv_kernel(const FusedArgs p, const int R) {
                 if (so[u] < 0) continue;
                 float wv = 0.0f, sv = 0.0f;
                 if (ok[u]) {
-                    const float sigma = (stoch || do_kl) ? softplus_sigma(rho[u]) : 0.0f;
+                    const float sigma = (stoch || do_kl) ? softplus_sigma_fast(rho[u]) : 0.0f;
                     if (LRT) { wv = mu[u]; sv = sigma * sigma; }
                     else if (stoch) {
                         const float e_ = p.eps_a ? __ldg(p.eps_a + wi[u]) : normal1(wi[u], nkey);
                         wv = mu[u] + e_ * sigma;
                     } else wv = mu[u];
-                    if (do_kl) kl_acc += (double)kl_term(mu[u], sigma, p.prior_mu, p.prior_sigma, p.kl_convention);
+                    if (do_kl) kl_acc += (double)kl_term_fast(mu[u], sigma, p.prior_mu, p.prior_sigma, p.kl_convention);
                 }
                 sm[so[u]] = __float2bfloat16_rn(wv);
                 if (p.planes == 2) sm[KHW * PS + so[u]] = __float2bfloat16_rn(sv);
@@ -226,13 +226,13 @@ tap_prep_conv_kernel(const FusedArgs p, const int R) {
             float bm = 0.0f, bv = 0.0f;
             if (p.has_bias && n < g.N) {
                 const float mu = __ldg(p.b_mu + n);
-                const float sigma = (stoch || do_kl) ? softplus_sigma(__ldg(p.b_rho + n)) : 0.0f;
+                const float sigma = (stoch || do_kl) ? softplus_sigma_fast(__ldg(p.b_rho + n)) : 0.0f;
                 if (LRT) { bm = mu; bv = sigma * sigma; }
                 else if (stoch) {
                     const float e_ = p.eps_b ? __ldg(p.eps_b + n) : normal1((uint64_t)g.N * g.K + n, nkey);
                     bm = mu + e_ * sigma;
                 } else bm = mu;
-                if (do_kl) kl_acc += (double)kl_term(mu, sigma, p.prior_mu, p.prior_sigma, p.kl_convention);
+                if (do_kl) kl_acc += (double)kl_term_fast(mu, sigma, p.prior_mu, p.prior_sigma, p.kl_convention);
             }
             p.bias_ws[n] = bm;
             p.bias_ws[npad + n] = bv;

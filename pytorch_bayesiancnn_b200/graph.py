@@ -50,10 +50,11 @@ class GraphedForward:
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graphs, self.outputs = [], []
+        cap = torch.cuda.Stream(device=dev, priority=-1)     # GEMM chain above the parameter preps on the (default-priority) side streams
         for xin in self.inputs:
             graph = torch.cuda.CUDAGraph()
             n0 = _lib.launch_count()
-            with torch.cuda.graph(graph), torch.no_grad(), Fn.workspace_slot(ws_slot):
+            with torch.cuda.graph(graph, stream=cap), torch.no_grad(), Fn.workspace_slot(ws_slot):
                 Fn.noise_advance(self.base, _STRIDE)
                 with Fn.stream_base(self.base):
                     out = net(xin)

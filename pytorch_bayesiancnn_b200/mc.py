@@ -179,10 +179,14 @@ class MCForward:
         into the sample buffer and hands over its per-layer KL scalars un-summed (fused.direct_output); with
         ``advance`` the exchange kernel also moves the Philox stream base for the next replay."""
         from . import fused
-        import os
+        from .graph import _STRIDE
         with torch.no_grad():
-            if advance and os.environ.get("BBB_MC_HEAD", "0") == "1":      # experiment: a leading kernel on the capture stream
-                Fn.noise_advance(base, 0)
+            if advance:
+                # the Philox base moves at the HEAD of a captured step.  (Measured: a captured step whose first kernel on
+                # the capture stream carries the programmatic-launch attribute but has no kernel before it loses the
+                # programmatic edges of the whole chain -- every GEMM then starts ~3.5 us after its predecessor ends,
+                # 129 vs 113 us per step; with this one-thread kernel in front the overlap is back.)
+                Fn.noise_advance(base, _STRIDE)
             kl_ptr, n_kl = None, 0
             if self.fold_steps is not None:
                 with Fn.stream_base(base), Fn.mc_sample(self.ids[0], self.seed):
@@ -204,7 +208,7 @@ class MCForward:
                         kl_ptr, n_kl = Fn._ptr(self.kl_one), 1
             if not self.ids and self.rank == 0:
                 raise L.EngineError("MCForward: rank 0 must own a sample")
-            self._exchange(kl_ptr, n_kl, base if advance else None)
+            self._exchange(kl_ptr, n_kl)
         return self.out
 
     def _exchange(self, kl_ptr, n_kl, advance_base=None):
@@ -229,15 +233,18 @@ class MCForward:
                 self._step(self.x, self.base)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        # GEMM chain on a HIGH-priority stream, parameter preps on the (default-priority) side streams: when both have CTAs
+        # pending, the chain's go first -- the preps of later layers no longer keep the first GEMM's CTAs off the SMs
+        cap = torch.cuda.Stream(device=dev, priority=-1)
         for xin in self.inputs:
             g = torch.cuda.CUDAGraph()
             n0 = L.launch_count()
-            with torch.cuda.graph(g):
-                self._step(xin, self.base, advance=True)           # the exchange kernel moves the noise base at the end of a step
+            with torch.cuda.graph(g, stream=cap):
+                self._step(xin, self.base, advance=True)
             self.kernels_per_step = L.launch_count() - n0          # engine kernels captured in one step
             self.graphs.append(g)
         self.graph = self.graphs[0]
-        self.base.fill_(self.first_replay * _STRIDE)
+        self.base.fill_((self.first_replay - 1) * _STRIDE)
 
     def __call__(self, x: Optional[torch.Tensor] = None, labels: Optional[torch.Tensor] = None, slot: int = 0):
         if labels is not None:

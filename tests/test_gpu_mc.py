@@ -271,7 +271,7 @@ def test_mc_forward_product_path_single_gpu(dev):
     # replay r draws streams base_r + sample namespace: reproduce replay 1 (the second) sample by sample, eagerly
     from pytorch_bayesiancnn_b200.graph import _STRIDE
     logits = []
-    base = torch.full((1,), _STRIDE, dtype=torch.int64, device=dev)         # replay 0 ran at base 0, replay 1 at base 2^20 (moved by the exchange kernel)
+    base = torch.full((1,), _STRIDE, dtype=torch.int64, device=dev)         # replay 0 ran at base 0, replay 1 at base 2^20 (moved by the head kernel of each replay)
     for j in range(4):
         with Fn.stream_base(base), Fn.mc_sample(j, 31), torch.no_grad():
             lg, kl = net(x)
