@@ -295,7 +295,7 @@ int bbb_layer_forward_fused(const bbb_layer_desc* d, const void* x, const void* 
         a.kl_counter = (unsigned int*)ws; a.kl_partials = (double*)((char*)ws + kCounterBytes); a.kl_out = kl_out;
         const size_t cpad = (size_t)(g.N + 63) / 64 * 64, kpad = (size_t)(g.Cin + 63) / 64 * 64;
         a.wtiles = (__nv_bfloat16*)((char*)ws + kTcOffset);
-        a.bias_ws = (float*)((char*)ws + kTcOffset + cpad * kpad * g.KHW * 4 + 16384);   // behind the zero sub-tile
+        a.bias_ws = (float*)((char*)ws + kTcOffset + cpad * kpad * g.KHW * 4 + 32768);   // behind the zero sub-tile
         a.prev_hw = prev_hw; a.y = y; a.y_sq = y_sq; a.out_mode = out_mode; a.out_pitch = out_pitch; a.pool = pool;
         a.in_pitch = in_pitch; a.trace = g_trace; a.fold = fold;
         a.tl_prep = tl_slot(!skip_prep, "tap_prep", g); a.tl_gemm = tl_slot(!prep_only, "tap_gemm", g);

@@ -51,7 +51,7 @@ __host__ __device__ inline size_t fused_wtile_elems(const FusedArgs& a) { return
 inline size_t fused_workspace_bytes(const Geom& g) {
     // worst case NG=16 padding of Cout, 2 planes
     const size_t cpad = (size_t)(g.N + 63) / 64 * 64, kpad = (size_t)(g.Cin + 63) / 64 * 64;
-    return cpad * kpad * g.KHW * 2 * 2 + 16384 /* zero sub-tile */ + 2 * cpad * 4;
+    return cpad * kpad * g.KHW * 2 * 2 + 32768 /* zero sub-tile (<= 2 planes x 128 rows x 128 B) */ + 2 * cpad * 4;
 }
 
 // ------------------------------------------------------------- (P) tap prep
@@ -264,7 +264,7 @@ static_assert(true, "");
 struct FusedSmem {
     unsigned long long full[4], empty[4], accum;
     uint32_t tmem_base, n_items;
-    float bias[64], bvar[64];       // this tile's 64 output columns
+    float bias[128], bvar[128];     // this tile's output columns (BN <= 128)
     // K-loop schedule, built once per CTA: x = ipix | kb << 16, y = the four column groups' taps (0xFF = outside the
     // kernel window -> zero sub-tile).  A pipeline step covers TAP_UNITS consecutive items: the fixed cost of a stage
     // hand-off (~500-900 cycles measured: barrier round trip + TMA issue + first-MMA start-up) is paid per STEP.
@@ -309,30 +309,33 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// TMEM columns of a tile: [0,64) mean accumulator, [64,128) variance accumulator (LRT), [128,192) the tile's LRT noise.
-// The noise tile is drawn (Philox) by the epilogue warps WHILE the main loop runs and parked in tensor memory: no
-// shared memory, no registers held across the main loop, and the epilogue stays a short rolled loop with static
-// register indices (a 64-value register array would force full unrolling; straight-line code that runs once per CTA
-// is what the cold instruction cache punishes -- DESIGN.md 5).
-constexpr uint32_t TAP_NOISE_COL = 128u;
-
+// TMEM columns of a tile (BN = tile width, 64 or 128): [0,BN) mean accumulator, [BN,2BN) variance accumulator (LRT),
+// [2BN,3BN) the tile's LRT noise.  The noise tile is drawn (Philox) by the epilogue warps WHILE the main loop runs and
+// parked in tensor memory: no shared memory, no registers held across the main loop, and the epilogue stays a short rolled
+// loop with static register indices (a 64-value register array would force full unrolling; straight-line code that runs
+// once per CTA is what the cold instruction cache punishes -- DESIGN.md 5).
+//
+// BN: every SS-mode tcgen05.mma pulls (128 + BN) * 32 B of operands out of shared memory at 64 B/clk (measured, DESIGN.md
+// 5), i.e. 96 cycles for the 32 cycles of math of an N=64 MMA, 128 for the 64 cycles of an N=128 one: the wider tile
+// raises the tensor-pipe ceiling from 1/3 to 1/2 and is used whenever it still leaves enough CTAs for the machine.
 // MINB = resident CTAs per SM the register allocation is sized for (1: configuration A, 2: configuration B)
-template <int MINB>
+template <int MINB, int BN>
 __global__ void __launch_bounds__(TAP_THREADS, MINB)
 tap_gemm_kernel(const FusedArgs p, const int stages) {
     extern __shared__ uint8_t smem_raw[];
+    constexpr uint32_t TB = BN * 128;                   // bytes of one B plane of a K block (BN rows x 64 bf16)
     const Geom& g = p.g;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int planes = p.planes;
     const bool two = planes == 2;
-    const int ng = p.ng, groups = 64 / ng;
+    const int ng = p.ng, groups = BN / ng;
 
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (base - raw);
     FusedSmem* ctl = reinterpret_cast<FusedSmem*>(sm);
     const uint32_t tiles_off = 2048u;
-    const uint32_t unit_bytes = (uint32_t)planes * (TC_A_BYTES + TC_B_BYTES);   // one K block: [A][A^2][B planes]
+    const uint32_t unit_bytes = (uint32_t)planes * (TC_A_BYTES + TB);   // one K block: [A][A^2][B planes]
     const int units = p.units;
     const uint32_t stage_bytes = (uint32_t)units * unit_bytes;
     const uint32_t a2_off = TC_A_BYTES, b_off = (uint32_t)planes * TC_A_BYTES;
@@ -385,7 +388,8 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
         ctl->n_items = (uint32_t)n;
     }
     const bool philox = two && !p.eps_a;
-    const uint32_t tmem_cols = philox ? 256u : (two ? 128u : 64u);
+    const uint32_t tmem_cols = philox ? 4u * BN : (two ? 2u * BN : (uint32_t)BN);     // power of two >= 3 BN when the noise tile lives there
+    constexpr uint32_t NOISE_COL = 2u * BN;
     if (warp == 8) tmem_alloc(smem_u32(&ctl->tmem_base), tmem_cols);
     tc_fence_before();
     __syncthreads();
@@ -433,7 +437,7 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
                     // x and x^2 blocks are interleaved in global memory and adjacent in the stage: one copy
                     const size_t a_blk = (a_row0 + (size_t)ipix * p.n_kblk + kb) * (size_t)(planes * 128 * 64);
                     bulk_g2s(st, reinterpret_cast<const __nv_bfloat16*>(p.x) + a_blk, a_copy, bar);
-                    // weight planes: [plane][group][ng rows x 128 B] -> every plane is one 64-row SW128 tile
+                    // weight planes: [plane][group][ng rows x 128 B] -> every plane is one BN-row SW128 tile
 #pragma unroll 1
                     for (int q = 0; q < groups; ++q) {
                         const int tp = (item.y >> (8 * q)) & 0xFF;
@@ -442,7 +446,7 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
                             bulk_g2s(st + b_off, sp, (uint32_t)planes * gbytes, bar);
                         } else {
                             bulk_g2s(st + b_off + q * gbytes, sp, gbytes, bar);
-                            if (two) bulk_g2s(st + b_off + TC_B_BYTES + q * gbytes, tp != 0xFF ? sp + ng * 64 : zero_tile, gbytes, bar);
+                            if (two) bulk_g2s(st + b_off + TB + q * gbytes, tp != 0xFF ? sp + ng * 64 : zero_tile, gbytes, bar);
                         }
                     }
                 }
@@ -452,7 +456,7 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
         }
     } else if (warp == 8) {
         // ======================= MMA issuer =====================================
-        const uint32_t idesc = make_idesc_bf16(TC_BM, 64);
+        const uint32_t idesc = make_idesc_bf16(TC_BM, BN);
         // descriptors are linear in the (address >> 4) field: build them once, add offsets per MMA
         const uint64_t dA0 = make_smem_desc_sw128(base + tiles_off);
         const uint64_t dB0 = make_smem_desc_sw128(base + tiles_off + b_off);
@@ -473,7 +477,7 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         umma_bf16(tmem, da + 2 * j, db + 2 * j, idesc, (it | u | j) ? 1u : 0u);
-                        if (two) umma_bf16(tmem + 64u, da + (a2_off >> 4) + 2 * j, db + (TC_B_BYTES >> 4) + 2 * j, idesc, (it | u | j) ? 1u : 0u);
+                        if (two) umma_bf16(tmem + (uint32_t)BN, da + (a2_off >> 4) + 2 * j, db + (TB >> 4) + 2 * j, idesc, (it | u | j) ? 1u : 0u);
                     }
                 }
                 umma_commit(smem_u32(&ctl->empty[s]));
@@ -485,22 +489,30 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
         tc_fence_before();
     } else {
         // ======================= epilogue (warps 0-7) ===========================
-        // thread = (tile row t = image, half h); it owns four chunks of 8 columns: chunk k starts at tile column
-        //   pool: k*16 + h*8  (pixel k of the 2x2 window, channels h*8 .. h*8+7 of the tile's 16)
-        //   else: h*32 + k*8  (the tile's single pixel, channels h*32 + k*8 ..)
+        // thread = (tile row t = image, half h).  Its columns, in chunks of 8:
+        //   pool: the tile holds ng channels x the 4 pixels of a 2x2 window (column = q*ng + channel); half h owns ng/2
+        //         channels = NC chunks, each present once per pixel q
+        //   else: the tile's single pixel, columns h*BN/2 + k*8
+        constexpr int NCH = BN / 16;                      // 8-column chunks per thread
         const int t = threadIdx.x & 127, h = threadIdx.x >> 7, b = m0 + t;
         const bool bvalid = b < g.B;
         const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-        const int n_base = p.pool ? cb * 16 + h * 8 : cb * 64 + h * 32;          // first output channel of chunk 0
+        const int nc = p.pool ? NCH / 4 : NCH;            // channel chunks this thread owns
+        // chunk index k -> (channel chunk cc, pixel group q): pool: k = cc*4 + q (the four pixels of a chunk are consecutive)
+        auto chunk_col = [&](int k, int& q, int& n0) {
+            if (p.pool) { const int cc = k >> 2; q = k & 3; n0 = cb * ng + h * (ng >> 1) + cc * 8; return q * ng + h * (ng >> 1) + cc * 8; }
+            q = 0; n0 = cb * BN + h * (BN / 2) + k * 8;
+            return h * (BN / 2) + k * 8;
+        };
         // (1) while the main loop runs: draw this row's LRT noise and park it in tensor memory
         if (philox) {
             int b_s = b;                                 // image index inside its MC sample
             const NoiseKey nkey = fold_key(effective_key(p.key, p.stream_base), p.fold, b, b_s);
 #pragma unroll 1
-            for (int k = 0; k < 4; ++k) {
-                int oh, ow;
-                group_pix(k, oh, ow);
-                const int n0 = p.pool ? n_base : n_base + k * 8;
+            for (int k = 0; k < NCH; ++k) {
+                int q, n0, oh, ow;
+                const int c0 = chunk_col(k, q, n0);
+                group_pix(q, oh, ow);
                 float z8[8];
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
@@ -508,16 +520,16 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
                     if (bvalid && n0 + 4 * hh < g.N) z = act_noise4(nkey, b_s, oh * g.OW + ow, n0 + 4 * hh, g.OHW, g.N);
                     z8[4 * hh] = z.x; z8[4 * hh + 1] = z.y; z8[4 * hh + 2] = z.z; z8[4 * hh + 3] = z.w;
                 }
-                tmem_st8(lane_base + TAP_NOISE_COL + (uint32_t)(p.pool ? k * 16 + h * 8 : h * 32 + k * 8), z8);
+                tmem_st8(lane_base + NOISE_COL + (uint32_t)c0, z8);
             }
             tmem_st_wait();
         }
         const bool any_mma = n_items > 0;  // did the schedule of warp 8 contain at least one step?
         // (2) accumulator ready
         pdl_wait();                                      // our output buffers may still be read by the previous step's consumer
-        if (threadIdx.x < 64) {                          // bias / bias variance of this tile's columns (written by the prep
+        if (threadIdx.x < BN) {                          // bias / bias variance of this tile's columns (written by the prep
             const int c = threadIdx.x;                   // kernel, which may be the programmatic predecessor: after the wait)
-            const int n = p.pool ? (cb * 16 + (c & 15)) : (cb * 64 + c);
+            const int n = p.pool ? (cb * ng + (c % ng)) : (cb * BN + c);
             ctl->bias[c] = p.bias_ws[n];
             ctl->bvar[c] = p.bias_ws[p.n_cblk * ng + n];
         }
@@ -526,20 +538,22 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
         tc_fence_after();
         if (tr && threadIdx.x == 0) tr[5] = clock64();
         const int ohw_out = p.pool ? (g.OHW >> 2) : g.OHW;
+        (void)nc;
         float r[8];
 #pragma unroll 1
-        for (int k = 0; k < 4; ++k) {
-            const int c0 = p.pool ? k * 16 + h * 8 : h * 32 + k * 8;          // tile column of this chunk
-            const int n0 = p.pool ? n_base : n_base + k * 8;                  // its first output channel
+        for (int k = 0; k < NCH; ++k) {
+            int q, n0;
+            const int c0 = chunk_col(k, q, n0);           // tile column / first output channel of this chunk
             float am[8];
-            tmem_ld8(lane_base + (uint32_t)c0, am);
+            tmem_ld8_nowait(lane_base + (uint32_t)c0, am);
             if (two) {
                 float av[8], e8[8];
-                tmem_ld8(lane_base + 64u + (uint32_t)c0, av);
-                if (philox) tmem_ld8(lane_base + TAP_NOISE_COL + (uint32_t)c0, e8);
-                else {
+                tmem_ld8_nowait(lane_base + (uint32_t)BN + (uint32_t)c0, av);
+                if (philox) tmem_ld8_nowait(lane_base + NOISE_COL + (uint32_t)c0, e8);
+                tmem_ld_wait();
+                if (!philox) {
                     int oh, ow;
-                    group_pix(k, oh, ow);
+                    group_pix(q, oh, ow);
 #pragma unroll
                     for (int u = 0; u < 8; ++u)
                         e8[u] = (bvalid && n0 + u < g.N) ? __ldg(p.eps_a + ((size_t)b * g.N + n0 + u) * g.OHW + oh * g.OW + ow) : 0.0f;
@@ -550,13 +564,14 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
                     am[u] = (any_mma ? am[u] : 0.0f) + ctl->bias[c0 + u] + fast_sqrt(var) * e8[u];
                 }
             } else {
+                tmem_ld_wait();
 #pragma unroll
                 for (int u = 0; u < 8; ++u) am[u] = (any_mma ? am[u] : 0.0f) + ctl->bias[c0 + u];
             }
-            if (p.pool) {                                 // 2x2 max over the four chunks, store after the last
+            if (p.pool) {                                 // 2x2 max over the chunk's four pixels, store after the last
 #pragma unroll
-                for (int u = 0; u < 8; ++u) r[u] = k ? fmaxf(r[u], am[u]) : am[u];
-                if (k < 3) continue;
+                for (int u = 0; u < 8; ++u) r[u] = q ? fmaxf(r[u], am[u]) : am[u];
+                if (q < 3) continue;
             } else {
 #pragma unroll
                 for (int u = 0; u < 8; ++u) r[u] = am[u];
@@ -573,14 +588,13 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
                         make_uint4(pack_bf16(r[0] * r[0], r[1] * r[1]), pack_bf16(r[2] * r[2], r[3] * r[3]),
                                    pack_bf16(r[4] * r[4], r[5] * r[5]), pack_bf16(r[6] * r[6], r[7] * r[7]));
             } else {
-#pragma unroll 1
+                float* yo = reinterpret_cast<float*>(p.y);
+#pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     const int n = n0 + u;
-                    if (n >= g.N) break;
-                    if (p.out_mode == OUT_ROWMAJOR_F32) {
-                        reinterpret_cast<float*>(p.y)[((size_t)b * ohw_out + pset) * g.N + n] = r[u];
-                    } else {
-                        reinterpret_cast<float*>(p.y)[((size_t)b * g.N + n) * ohw_out + pset] = r[u];
+                    if (n < g.N) {
+                        if (p.out_mode == OUT_ROWMAJOR_F32) yo[((size_t)b * ohw_out + pset) * g.N + n] = r[u];
+                        else yo[((size_t)b * g.N + n) * ohw_out + pset] = r[u];
                     }
                 }
             }
@@ -610,10 +624,18 @@ inline cudaError_t launch_fused(FusedArgs a, const void* x, const void* x_sq, cu
     const Geom& g = a.g;
     *n_launch = 0;
     a.planes = tc_planes(a.variant, a.sample);
-    a.ng = a.pool ? 16 : 64;
-    a.n_cblk = (g.N + a.ng - 1) / a.ng;
-    a.n_kblk = (g.Cin + 63) / 64;
-    a.taps = g.KHW;
+    // tile width: 128 columns when Cout allows it and the grid still covers most of the machine (operand bytes per MAC,
+    // see tap_gemm_kernel), else 64.  BBB_B200_TAP_BN=64 forces the narrow tile (A/B measurements).
+    const int psets = a.pool ? (g.OH / 2) * (g.OW / 2) : g.OHW;
+    const int row_tiles = (g.B + TC_BM - 1) / TC_BM;
+    int bn = 64;
+    {
+        static const int force = [] { const char* e = getenv("BBB_B200_TAP_BN"); return e ? atoi(e) : 0; }();
+        const int ng128 = a.pool ? 32 : 128;
+        if (g.N % ng128 == 0 && (long)psets * (g.N / ng128) * row_tiles >= (long)n_sm * 6 / 10) bn = 128;
+        if (force == 64 || force == 128) bn = (force == 128 && g.N % ng128 == 0) ? 128 : 64;
+    }
+    a.ng = a.pool ? bn / 4 : bn;
     const bool lrt = a.variant == BBB_VARIANT_LRT;
     a.x = x; a.x_sq = x_sq;
     if (do_gemm && a.planes == 2 && x_sq != (const void*)((const __nv_bfloat16*)x + 128 * 64)) {
@@ -662,18 +684,20 @@ inline cudaError_t launch_fused(FusedArgs a, const void* x, const void* x_sq, cu
         *n_launch += 1;
     }
     if (!do_gemm) return cudaSuccess;
-    // Two configurations.  (A) one CTA per SM: stage = 2 K blocks, deep ring.  (B) two CTAs per SM (~99 KB each): used when
-    // the grid has more CTAs than SMs (AlexNet conv2: 192), so that all tiles run in ONE wave and one CTA's epilogue
-    // overlaps the other's main loop.  In both the LRT noise tile is drawn into tensor memory during the main loop.
-    const int psets = a.pool ? (g.OH / 2) * (g.OW / 2) : g.OHW;
-    const long n_ctas = (long)psets * a.n_cblk * ((g.B + TC_BM - 1) / TC_BM);
-    const bool two_per_sm = n_ctas > n_sm;
+    // Configurations.  BN = 64: (A) one CTA per SM, stage = 2 K blocks, deep ring; (B) two CTAs per SM (~99 KB each) when
+    // the grid has more CTAs than SMs, so that all tiles run in ONE wave and one CTA's epilogue overlaps the other's main
+    // loop.  BN = 128: one CTA per SM, 64 KB (LRT) / 32 KB K blocks, three stages.  The LRT noise tile always lives in
+    // tensor memory and is drawn during the main loop.
+    const long n_ctas = (long)psets * a.n_cblk * row_tiles;
+    const bool two_per_sm = bn == 64 && n_ctas > n_sm;
     int stages;
-    if (two_per_sm) { stages = 2; a.units = a.planes == 2 ? 1 : 2; }
-    else            { stages = a.planes == 2 ? 2 : 4; a.units = TAP_UNITS; }
+    if (bn == 128)       { stages = 3; a.units = a.planes == 2 ? 1 : 2; }
+    else if (two_per_sm) { stages = 2; a.units = a.planes == 2 ? 1 : 2; }
+    else                 { stages = a.planes == 2 ? 2 : 4; a.units = TAP_UNITS; }
     if (const char* e = getenv("BBB_B200_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= stages) stages = v; }
-    const size_t smem = 1023 + 2048 + (size_t)stages * a.units * tc_stage_bytes(a.planes);   // align slack + control/schedule + ring
-    dim3 grid(psets * a.n_cblk, (g.B + TC_BM - 1) / TC_BM);
+    const size_t unit_bytes = (size_t)a.planes * (TC_A_BYTES + (size_t)bn * 128);
+    const size_t smem = 1023 + 2048 + (size_t)stages * a.units * unit_bytes;   // align slack + control/schedule + ring
+    dim3 grid(psets * a.n_cblk, row_tiles);
     cudaError_t e;
     auto launch = [&](auto kernel) {
         cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -681,7 +705,7 @@ inline cudaError_t launch_fused(FusedArgs a, const void* x, const void* x_sq, cu
         if (e2 != cudaSuccess) return e2;
         return launch_pdl(kernel, grid, dim3(TAP_THREADS), smem, st, a, stages);
     };
-    e = two_per_sm ? launch(tap_gemm_kernel<2>) : launch(tap_gemm_kernel<1>);
+    e = bn == 128 ? launch(tap_gemm_kernel<1, 128>) : (two_per_sm ? launch(tap_gemm_kernel<2, 64>) : launch(tap_gemm_kernel<1, 64>));
     if (e != cudaSuccess) return e;
     e = cudaGetLastError();
     if (e == cudaSuccess) *n_launch += 1;
