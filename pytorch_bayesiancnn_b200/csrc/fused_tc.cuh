@@ -636,6 +636,9 @@ inline cudaError_t launch_fused(FusedArgs a, const void* x, const void* x_sq, cu
         if (force == 64 || force == 128) bn = (force == 128 && g.N % ng128 == 0) ? 128 : 64;
     }
     a.ng = a.pool ? bn / 4 : bn;
+    a.n_cblk = (g.N + a.ng - 1) / a.ng;
+    a.n_kblk = (g.Cin + 63) / 64;
+    a.taps = g.KHW;
     const bool lrt = a.variant == BBB_VARIANT_LRT;
     a.x = x; a.x_sq = x_sq;
     if (do_gemm && a.planes == 2 && x_sq != (const void*)((const __nv_bfloat16*)x + 128 * 64)) {
