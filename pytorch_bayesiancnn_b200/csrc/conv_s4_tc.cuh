@@ -27,7 +27,10 @@
 
 namespace bbb {
 
-constexpr int S4_IMGS = 16, S4_WIN_PX = 12, S4_KROW = 48, S4_THREADS = 320, S4_STAGES = 4;
+constexpr int S4_IMGS = 16, S4_WIN_PX = 12, S4_KROW = 48, S4_THREADS = 320;
+// weight ring depth: three 12 KB stages keep the CTA at ~193 KB, so that one weight-prep CTA of a later layer (<= 26 KB,
+// launch_fused) can share the SM -- with four stages every prep CTA kept a conv_s4 CTA off its SM until it had drained
+constexpr int S4_STAGES = 3;
 constexpr int S4_BPLANE = 64 * S4_KROW * 2;                // one plane of one kernel row: 6 chunks x 64 rows x 16 B = 6144 B
 
 struct S4Args {

@@ -258,6 +258,78 @@ def out_hw(h, w, kh, kw, conv):
 
 
 # --------------------------------------------------------------------------- #
+# tensor-core backward: wgrad / dgrad as role-swapped calls of the tcgen05 layer kernel
+# --------------------------------------------------------------------------- #
+_TC_K_MAX = 8192          # the gather kernel keeps an 8-byte table entry per reduction index in shared memory
+
+
+def _tc_contract(x, w, conv):
+    """Plain (mean-only, bias-free) conv2d / linear of fp32 `x` with the fp32 tensor `w` on the tcgen05 layer kernel
+    (bf16 operands, fp32 TMEM accumulators): the engine's forward with sample=0 and no KL."""
+    lib = L.lib()
+    x, w = x.contiguous(), w.contiguous()
+    d = make_desc(tuple(x.shape), tuple(w.shape), conv, L.VARIANT_BBB, False, False, 0.0, 1.0, L.MATH_BF16_TC)
+    if conv is None:
+        y = torch.empty(x.shape[0], w.shape[0], dtype=torch.float32, device=x.device)
+        fn = lib.bbb_linear_forward
+    else:
+        oh, ow = out_hw(x.shape[2], x.shape[3], w.shape[2], w.shape[3], conv)
+        y = torch.empty(x.shape[0], w.shape[0], oh, ow, dtype=torch.float32, device=x.device)
+        fn = lib.bbb_conv2d_forward
+    ws = workspace(x.device, d)
+    rc = fn(C.byref(d), _ptr(x), _ptr(w), _ptr(w), None, None, _ptr(y), None, None, None, None,
+            C.c_uint64(0), C.c_uint64(0), None, _ptr(ws), C.c_size_t(ws.numel()), _stream(x.device))
+    L.check(rc, "tcgen05 contraction (backward)")
+    return y
+
+
+def _tc_dgrad(g, w, conv, x_shape):
+    """d x of y = conv(x, w): the full correlation of (zero-inserted) g with the flipped, channel-transposed kernel --
+    itself a stride-1 convolution, so it runs on the same tcgen05 layer kernel."""
+    if conv is None:
+        return _tc_contract(g, w.t(), None)                               # [B,N] x [K,N]^T -> [B,K]
+    (sh, sw), (ph, pw), (dh, dw) = conv
+    kh, kw = w.shape[2], w.shape[3]
+    H, W = x_shape[2], x_shape[3]
+    OH, OW = g.shape[2], g.shape[3]
+    qh, qw = dh * (kh - 1) - ph, dw * (kw - 1) - pw
+    if qh < 0 or qw < 0:
+        return None
+    hup = H - (dh * (kh - 1) - 2 * ph)                # rows of the zero-inserted gradient map: hup + 2*qh - dh*(kh-1) == H
+    wup = W - (dw * (kw - 1) - 2 * pw)
+    if (sh, sw) != (1, 1) or hup != OH or wup != OW:
+        gu = g.new_zeros(g.shape[0], g.shape[1], hup, wup)
+        gu[:, :, 0:(OH - 1) * sh + 1:sh, 0:(OW - 1) * sw + 1:sw] = g
+        g = gu
+    wt = w.flip(2, 3).transpose(0, 1)
+    return _tc_contract(g, wt, ((1, 1), (qh, qw), (dh, dw)))
+
+
+def _tc_wgrad(x, g, conv, w_shape):
+    """d w of y = conv(x, w): a convolution with the batch as the reduction ("channel") axis -- input x^T [C,B,H,W],
+    kernel g^T [N,B,OH,OW], stride <-> dilation swapped -- on the tcgen05 layer kernel.  Deterministic (no atomics);
+    the batch is cut so that the reduction index fits the kernel's shared-memory table and the partial results summed."""
+    if conv is None:
+        out = _tc_contract(x.t(), g.t(), None)                             # [K,B] x [N,B]^T -> [K,N]
+        return out.t()
+    (sh, sw), (ph, pw), (dh, dw) = conv
+    kh, kw = w_shape[2], w_shape[3]
+    B = x.shape[0]
+    per = max(1, _TC_K_MAX // (g.shape[2] * g.shape[3]))
+    acc = None
+    for b0 in range(0, B, per):
+        xt = x[b0:b0 + per].transpose(0, 1)
+        gt = g[b0:b0 + per].transpose(0, 1)
+        part = _tc_contract(xt, gt, ((dh, dw), (ph, pw), (sh, sw)))[:, :, :kh, :kw]
+        acc = part if acc is None else acc + part
+    return acc.transpose(0, 1)
+
+
+def _tc_backward_ok(cfg):
+    return cfg["math"] in (L.MATH_BF16_TC, L.MATH_AUTO) and os.environ.get("BBB_B200_BWD", "tc") != "simt"
+
+
+# --------------------------------------------------------------------------- #
 # the layer op
 # --------------------------------------------------------------------------- #
 class BayesLayerFn(torch.autograd.Function):
@@ -334,7 +406,23 @@ class BayesLayerFn(torch.autograd.Function):
         g_b_mu = torch.zeros_like(bias_mu) if ctx.has_bias else None
         g_b_rho = torch.zeros_like(bias_rho) if ctx.has_bias else None
         gx = None
-        if gy is not None:
+        done = False
+        if gy is not None and _tc_backward_ok(cfg):
+            try:
+                out = BayesLayerFn._backward_tc(ctx, gy.contiguous().float())
+            except L.EngineError as e:
+                if "code -2" not in str(e):                # BBB_E_UNSUPPORTED: a shape the tcgen05 kernel does not take
+                    raise
+                out = None
+            if out is not None:
+                gx, gw_mu, gw_rho, gb_mu, gb_rho = out
+                g_W_mu += gw_mu.reshape(g_W_mu.shape)
+                g_W_rho += gw_rho.reshape(g_W_rho.shape)
+                if ctx.has_bias:
+                    g_b_mu += gb_mu
+                    g_b_rho += gb_rho
+                done = True
+        if gy is not None and not done:
             gy = gy.contiguous().float()
             if ctx.needs_input_grad[0]:
                 gx = torch.zeros_like(x)
@@ -360,6 +448,75 @@ class BayesLayerFn(torch.autograd.Function):
                                          _stream(dev))
                 L.check(rc, "bbb_kl_backward")
         return gx, g_W_mu, g_W_rho, g_b_mu, g_b_rho, None
+
+
+    @staticmethod
+    def _backward_tc(ctx, gy):
+        """SURVEY.md Appendix A on the tensor cores: every contraction of the backward (wgrad of the mean and of the
+        variance path, dgrad of both) is a call of the tcgen05 layer kernel with the operands' roles swapped; eps is
+        regenerated from the forward's Philox stream; the element-wise chain rule through sigma = softplus(rho) is
+        parameter-sized glue.  Returns None when a shape does not fit (the caller then uses the CUDA-core kernels)."""
+        x, W_mu, W_rho, bias_mu, bias_rho, act_std, eps_a, eps_b = ctx.saved_tensors
+        cfg = ctx.cfg
+        conv, variant, sample = cfg["conv"], cfg["variant"], cfg["sample"]
+        dev = x.device
+        seed, stream_id, base = ctx.noise
+        if base is not None:
+            stream_id = int(stream_id) + int(base.item())
+        need_x = ctx.needs_input_grad[0]
+        sig = torch.log1p(torch.exp(W_rho))
+        dsig = torch.sigmoid(W_rho)
+        gb_mu = gb_rho = None
+        red = (0,) if conv is None else (0, 2, 3)
+        if variant == L.VARIANT_LRT:
+            gw_mu = _tc_wgrad(x, gy, conv, W_mu.shape)
+            if sample:
+                if eps_a is None:
+                    z = philox_normal(gy.numel(), seed, stream_id, 0, device=dev)
+                    eps = z.view(gy.shape) if conv is None else z.view(gy.shape[0], gy.shape[2], gy.shape[3], gy.shape[1]).permute(0, 3, 1, 2)
+                else:
+                    eps = eps_a
+                gv = gy * eps / (2.0 * act_std)
+                gw_rho = _tc_wgrad(x * x, gv, conv, W_mu.shape) * (2.0 * sig * dsig)
+            else:
+                gv, gw_rho = None, torch.zeros_like(W_rho)
+            gx = None
+            if need_x:
+                gx = _tc_dgrad(gy, W_mu, conv, x.shape)
+                if gx is None:
+                    return None
+                if sample:
+                    gx2 = _tc_dgrad(gv, sig * sig, conv, x.shape)
+                    gx = gx + 2.0 * x * gx2
+            if ctx.has_bias:
+                gb_mu = gy.sum(red)
+                if sample:
+                    sb = torch.log1p(torch.exp(bias_rho))
+                    gb_rho = gv.sum(red) * (2.0 * sb * torch.sigmoid(bias_rho))
+                else:
+                    gb_rho = torch.zeros_like(bias_rho)
+        else:
+            nw = W_mu.numel()
+            if sample:
+                ew = eps_a if eps_a is not None else philox_normal(nw, seed, stream_id, 0, device=dev).view(W_mu.shape)
+                W = W_mu + ew * sig
+            else:
+                ew, W = None, W_mu
+            gw_mu = _tc_wgrad(x, gy, conv, W_mu.shape)
+            gw_rho = gw_mu.reshape(W_mu.shape) * ew * dsig if sample else torch.zeros_like(W_rho)
+            gx = None
+            if need_x:
+                gx = _tc_dgrad(gy, W, conv, x.shape)
+                if gx is None:
+                    return None
+            if ctx.has_bias:
+                gb_mu = gy.sum(red)
+                if sample:
+                    eb = eps_b if eps_b is not None else philox_normal(bias_mu.numel(), seed, stream_id, nw, device=dev)
+                    gb_rho = gb_mu * eb * torch.sigmoid(bias_rho)
+                else:
+                    gb_rho = torch.zeros_like(bias_rho)
+        return gx, gw_mu, gw_rho, gb_mu, gb_rho
 
 
 class KLFn(torch.autograd.Function):
