@@ -26,7 +26,7 @@ char g_tl_names[256][64];
 long long* tl_slot(bool used, const char* kind, const bbb::Geom& g) {
     if (!g_tl || !used || g_tl_n >= g_tl_cap || g_tl_n >= 256) return nullptr;
     snprintf(g_tl_names[g_tl_n], sizeof(g_tl_names[0]), "%s M=%d N=%d K=%d", kind, g.M, g.N, g.K);
-    return g_tl + 2 * (g_tl_n++);
+    return g_tl + 4 * (g_tl_n++);
 }
 
 int fail(int code, const char* fmt, ...) {
@@ -462,7 +462,7 @@ int bbb_noise_advance(uint64_t* base, uint64_t inc, void* cuda_stream) {
 
 /* debug only (not in the public header): per-CTA clock64 checkpoints of tap_gemm_kernel */
 void bbb_debug_set_trace(void* dev_ptr) { g_trace = (long long*)dev_ptr; }
-/* debug only: timeline slots (2 x int64 per instrumented launch; caller presets [INT64_MAX, 0] before a run) */
+/* debug only: timeline slots (4 x int64 per instrumented launch; caller presets [INT64_MAX, 0, INT64_MAX, 0] before a run) */
 void bbb_debug_set_timeline(void* dev_ptr, int capacity) { g_tl = (long long*)dev_ptr; g_tl_cap = capacity; g_tl_n = 0; }
 int bbb_debug_timeline_count(void) { return g_tl_n; }
 const char* bbb_debug_timeline_name(int k) { return (k >= 0 && k < g_tl_n) ? g_tl_names[k] : ""; }

@@ -187,8 +187,10 @@ __device__ __forceinline__ void kl_publish(double partial, int slot, int n_slots
 }
 
 
-// Debug timeline (bbb_debug_set_timeline): every instrumented launch owns two 64-bit slots,
-// [0] = earliest CTA entry, [1] = latest CTA exit, in %globaltimer nanoseconds.  nullptr in production.
+// Debug timeline (bbb_debug_set_timeline): every instrumented launch owns four 64-bit slots,
+// [0] = earliest CTA entry, [1] = latest CTA exit, [2] = earliest moment a CTA got past griddepcontrol.wait (kernels
+// launched with programmatic serialization enter while their predecessor still runs: [1] - [2] is the part of the
+// kernel that sits on the critical path), [3] unused; %globaltimer nanoseconds.  nullptr in production.
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -196,6 +198,9 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 }
 __device__ __forceinline__ void tl_enter(long long* tl, int tid = 0) {
     if (tl && threadIdx.x == tid) atomicMin((unsigned long long*)tl, globaltimer_ns());
+}
+__device__ __forceinline__ void tl_dep(long long* tl, int tid = 0) {
+    if (tl && threadIdx.x == tid) atomicMin((unsigned long long*)tl + 2, globaltimer_ns());
 }
 __device__ __forceinline__ void tl_exit(long long* tl, int tid = 0) {
     if (tl && threadIdx.x == tid) atomicMax((unsigned long long*)tl + 1, globaltimer_ns());

@@ -171,6 +171,7 @@ conv_s4_kernel(const S4Args p) {
     const uint32_t tmem_cols = (two && !p.eps_a) ? 512u : (two ? 256u : 128u);      // accumulators (+ the LRT noise tile)
     if (warp == 8) tmem_alloc(smem_u32(&ctl->tmem_base), tmem_cols);
     pdl_wait();                                                  // everything below reads / writes tensors other kernels touch
+    tl_dep(p.tl_gemm);
     if (threadIdx.x < 64) {
         ctl->bias[threadIdx.x] = p.bias_ws[threadIdx.x];
         ctl->bvar[threadIdx.x] = p.bias_ws[64 + threadIdx.x];

@@ -413,6 +413,7 @@ tap_gemm_kernel(const FusedArgs p, const int stages) {
         const int pid = warp - 9;
         const int nprod = min(TAP_NPROD, stages);
         pdl_wait();                                      // A / A^2 are the previous layer's output
+        tl_dep(p.tl_gemm, 288);
         const size_t sub_elems = (size_t)planes * ng * 64;
         const __nv_bfloat16* zero_tile = p.wtiles + (size_t)p.taps * p.n_cblk * p.n_kblk * sub_elems;
         const uint32_t gbytes = (uint32_t)ng * 128;                     // one group, one plane

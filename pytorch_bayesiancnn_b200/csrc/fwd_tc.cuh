@@ -403,6 +403,7 @@ gemm_tc_kernel(const TcArgs p, const int stages) {
         ktab[k] = e;
     }
     pdl_wait();                                         // everything below reads/writes tensors other kernels touch
+    tl_dep(p.tl_gemm);
     if (p.stage_x) {
         // the tile's input images, loaded once and coalesced; the im2col gather then reads shared memory
         // (LDS latency ~30 cycles) instead of issuing 64 dependent-latency global loads per thread and k-block

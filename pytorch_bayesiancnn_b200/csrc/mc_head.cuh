@@ -77,6 +77,7 @@ mc_exchange_kernel(const McxArgs p) {
     const int b0 = blockIdx.x * rows_per_cta, b1 = min(B, b0 + rows_per_cta);
     tl_enter(p.tl);
     asm volatile("griddepcontrol.wait;" ::: "memory");      // launched with programmatic serialization: the logits come from the predecessor
+    tl_dep(p.tl);
     if (threadIdx.x == 0) seq_sh = *p.seq + 1u;
     __syncthreads();
     const unsigned int seq = seq_sh;

@@ -36,7 +36,7 @@ if MC:
 else:
     bbb.GraphedForward(net, xs[0])
 CAP = 64
-slots = torch.zeros(CAP, 2, dtype=torch.int64, device=dev)
+slots = torch.zeros(CAP, 4, dtype=torch.int64, device=dev)
 lib.bbb_debug_set_timeline(C.c_void_p(slots.data_ptr()), CAP)
 if MC:
     class _G:                                                    # capture only (the eager warm-up steps inside consume slots too:
@@ -49,7 +49,7 @@ n = lib.bbb_debug_timeline_count()
 names = [lib.bbb_debug_timeline_name(k).decode() for k in range(n)]
 lib.bbb_debug_set_timeline(None, 0)
 
-init = torch.tensor([[2 ** 62, 0]] * CAP, dtype=torch.int64, device=dev)
+init = torch.tensor([[2 ** 62, 0, 2 ** 62, 0]] * CAP, dtype=torch.int64, device=dev)
 runs, ev_us = [], []
 for rep in range(30):
     g.inputs[0].copy_(xs[rep % 24])                              # fresh (L2-cold) input each replay, like bench.py
@@ -61,15 +61,16 @@ for rep in range(30):
     ev_us.append(e0.elapsed_time(e1) * 1e3)
     t = slots[:n].cpu()
     t0 = int(t[:, 0].min())
-    runs.append(((t[:, 0] - t0).tolist(), (t[:, 1] - t0).tolist()))
+    runs.append(((t[:, 0] - t0).tolist(), (t[:, 1] - t0).tolist(), (torch.minimum(t[:, 2], t[:, 1]) - t0).tolist()))
 print(f"BBBAlexNet {variant} B={B}: event-timed replay median {statistics.median(ev_us):.1f} us "
       f"(min {min(ev_us):.1f}); {n} instrumented launches per replay")
 med = lambda k, j: statistics.median(r[j][k] for r in runs[5:]) / 1e3
 order = sorted(range(n), key=lambda k: med(k, 0))
-print(f"{'kernel':44s} {'start us':>9s} {'end us':>9s} {'dur us':>8s}")
+print(f"{'kernel':44s} {'start us':>9s} {'end us':>9s} {'dur us':>8s} {'deps ok':>8s} {'work us':>8s}")
 order = [k for k in order if med(k, 1) > 0 and med(k, 0) < 1e6]     # slots the replay really wrote
 for k in order:
-    print(f"{names[k]:44s} {med(k, 0):9.1f} {med(k, 1):9.1f} {med(k, 1) - med(k, 0):8.1f}")
+    dep = med(k, 2) if med(k, 2) < 1e6 else med(k, 0)
+    print(f"{names[k]:44s} {med(k, 0):9.1f} {med(k, 1):9.1f} {med(k, 1) - med(k, 0):8.1f} {dep:8.1f} {med(k, 1) - dep:8.1f}")
 gemm = [k for k in order if "gemm" in names[k] or "conv_s4 " in names[k]]
 print("GEMM critical path: " + "  ".join(
     f"[{names[k].split()[0]} {med(k, 1) - med(k, 0):.1f}]" + (f" gap {med(gemm[i + 1], 0) - med(k, 1):.1f}" if i + 1 < len(gemm) else "")
