@@ -130,7 +130,7 @@ __device__ __noinline__ float kl_term(float mu, float sigma, float pm, float ps,
 // BBBAlexNet) while sharing the machine with the GEMM chain: ~3x fewer instructions.  sigma keeps log1pf (the argument
 // is ~1e-2: a plain log(1 + x) would lose 4 digits); the KL term uses one reciprocal instead of three divisions and the
 // MUFU logarithm, whose ~1e-6 absolute error is far inside the 1e-5 relative bar of a sum of O(1)..O(100) terms
-// (measured against the float64 oracle: tests/test_gpu_parity.py).
+// (checked by the KL parity tests, tests/test_gpu_parity.py).
 __device__ __forceinline__ float softplus_sigma_fast(float rho) { return log1pf(__expf(rho)); }
 __device__ __forceinline__ float kl_term_fast(float mu, float sigma, float pm, float ps, int convention) {
     const float inv = __frcp_rn(sigma);

@@ -667,9 +667,9 @@ inline cudaError_t launch_fused(FusedArgs a, const void* x, const void* x_sq, cu
         auto need = [&](int r) { return (size_t)a.planes * g.KHW * prep2_slab(r) * 2; };
         // <= 26 KB of staging per CTA: the preps run beside the GEMM chain (side streams) and must fit next to its CTAs
         constexpr size_t kPrepSmem = 26 * 1024;
-        // ... and enough CTAs to keep loads in flight: the kernel is latency-bound (each thread has only a few dependent
-        // load batches), so it wants >= ~4 CTAs per SM, not big ones (measured: 20 us per layer with 48-192 CTAs)
-        while (R > 1 && ((long)(npad / R) * a.n_kblk < 4L * n_sm || need(R) > kPrepSmem)) R >>= 1;
+        // (smaller CTAs -- >= 4 per SM -- were tried for more loads in flight: the preps then lose the scheduling race against
+        //  the high-priority GEMM chain and the third layer's prep finished at 61 us instead of 21 us: 123 vs 107 us per step)
+        while (R > 2 && ((long)(npad / R) * a.n_kblk < n_sm || need(R) > kPrepSmem)) R >>= 1;
         const bool prep2 = prep2_on && g.KHW > 1 && a.prev_hw == 1 && g.Cin % 64 == 0 && a.taps == g.KHW && need(R) <= 48 * 1024;
         if (prep2) {
             static const bool carve2 = [] {

@@ -173,12 +173,14 @@ class direct_output:
     kernel sums them: bbb_mc_exchange), so the Monte-Carlo step has no copy and no aten reduction behind the chain.
     ``.used`` tells whether a fused chain really took the buffer (non-fusable nets ignore the hook)."""
 
-    def __init__(self, out):
-        self.out, self.used = out, False
+    def __init__(self, out, after_fork=None):
+        """``after_fork``: called once on the main stream right after the parameter-prep side streams have forked and
+        before the first GEMM is enqueued (e.g. the step's noise-advance kernel, which LRT preps do not depend on)."""
+        self.out, self.used, self.after_fork = out, False, after_fork
 
     def __enter__(self):
         self.prev = dict(_direct)
-        _direct.update(out=self.out, terms=True, owner=self)
+        _direct.update(out=self.out, terms=True, owner=self, after_fork=self.after_fork)
         return self
 
     def __exit__(self, *exc):
@@ -199,10 +201,11 @@ def _prep_chains():
 
 
 def run(steps, x: torch.Tensor, overlap_prep: bool = True):
-    return _run(steps, x, overlap_prep, _direct.get("out"), _direct.get("terms", False), _direct.get("owner"))
+    return _run(steps, x, overlap_prep, _direct.get("out"), _direct.get("terms", False), _direct.get("owner"),
+                after_fork=_direct.get("after_fork"))
 
 
-def _run(steps, x, overlap_prep, out, terms, owner, fold=None):
+def _run(steps, x, overlap_prep, out, terms, owner, fold=None, after_fork=None):
     """Execute a planned chain.  Returns (network output fp32, summed KL 0-dim tensor).
 
     The parameter-only half of every layer (softplus / eps / bf16 operand tiles / KL) runs on side
@@ -226,6 +229,9 @@ def _run(steps, x, overlap_prep, out, terms, owner, fold=None):
             for side in chains:
                 side.wait_stream(main)
             forked = True
+            if after_fork is not None:
+                after_fork()
+                after_fork = None
             events = []
             for i, st in enumerate(steps):
                 side = chains[i % len(chains)]
@@ -239,6 +245,8 @@ def _run(steps, x, overlap_prep, out, terms, owner, fold=None):
             if not terms:
                 with torch.cuda.stream(chains[0]):
                     kl_total = kls.sum()
+        if after_fork is not None:
+            after_fork()
         cur, cur_sq, cur_pitch = x.contiguous().float(), None, 0
         last = steps[-1]
         take = (out is not None and last.out_layout == L.LAYOUT_ROWMAJOR_F32 and out.is_contiguous()

@@ -120,14 +120,16 @@ class MCForward:
         # row drawing from its own sample's Philox stream; the KL is computed once.  BBB nets (a weight draw per sample)
         # and nets the chain cannot take run sample by sample.
         self.fold_steps = None
-        if fold and len(self.ids) > 1:
-            from . import fused
-            from .modules import _BayesLayer
-            kids = list(net.children())
-            layers = [m_ for m_ in kids if isinstance(m_, _BayesLayer)]
-            if layers and all(m_._variant == L.VARIANT_LRT for m_ in layers) and getattr(net, "fuse", True):
-                self.fold = (self.B, self.world << 40)
-                self.fold_steps = fused.plan(kids, (len(self.ids) * self.B,) + tuple(example_x.shape[1:]), self.fold)
+        from . import fused
+        from .modules import _BayesLayer
+        kids = list(net.children())
+        layers = [m_ for m_ in kids if isinstance(m_, _BayesLayer)]
+        all_lrt = bool(layers) and all(m_._variant == L.VARIANT_LRT for m_ in layers) and getattr(net, "fuse", True)
+        if fold and len(self.ids) > 1 and all_lrt:
+            self.fold = (self.B, self.world << 40)
+            self.fold_steps = fused.plan(kids, (len(self.ids) * self.B,) + tuple(example_x.shape[1:]), self.fold)
+        # an all-LRT net that runs as a fused chain: its weight preps do not depend on the step's noise base
+        self._lrt_chain = all_lrt and (self.fold_steps is not None or fused.plan(kids, tuple(example_x.shape)) is not None)
         self.graph, self.graphs = None, []
         self.replays = 0
         self.kernels_per_step = None
@@ -181,21 +183,26 @@ class MCForward:
         from . import fused
         from .graph import _STRIDE
         with torch.no_grad():
-            if advance:
-                # the Philox base moves at the HEAD of a captured step.  (Measured: a captured step whose first kernel on
-                # the capture stream carries the programmatic-launch attribute but has no kernel before it loses the
-                # programmatic edges of the whole chain -- every GEMM then starts ~3.5 us after its predecessor ends,
-                # 129 vs 113 us per step; with this one-thread kernel in front the overlap is back.)
-                Fn.noise_advance(base, _STRIDE)
+            # The Philox base moves at the HEAD of a captured step.  (Measured: a captured step whose first kernel on the
+            # capture stream carries the programmatic-launch attribute but has no kernel before it loses the programmatic
+            # edges of the whole chain -- every GEMM then starts ~3.5 us after its predecessor ends, 129 vs 113 us per
+            # step; with this one-thread kernel in front the overlap is back.)  LRT weight preps do not read the noise
+            # base, so for an all-LRT fused chain the kernel is enqueued AFTER the prep streams have forked: the preps
+            # start at once instead of behind it.
+            adv = (lambda: Fn.noise_advance(base, _STRIDE)) if advance else None
+            late = adv is not None and self._lrt_chain
+            if adv is not None and not late:
+                adv()
             kl_ptr, n_kl = None, 0
             if self.fold_steps is not None:
                 with Fn.stream_base(base), Fn.mc_sample(self.ids[0], self.seed):
                     _, kls = fused._run(self.fold_steps, x, True, self.logits.view(len(self.ids) * self.B, self.C), True, None,
-                                        fold=self.fold)
+                                        fold=self.fold, after_fork=adv if late else None)
                 self._kl_terms = kls
                 kl_ptr, n_kl = Fn._ptr(kls), kls.numel()
             for k, j in enumerate(self.ids if self.fold_steps is None else ()):
-                with Fn.stream_base(base), Fn.mc_sample(j, self.seed), fused.direct_output(self.logits[k]) as hook:
+                with Fn.stream_base(base), Fn.mc_sample(j, self.seed), \
+                        fused.direct_output(self.logits[k], adv if (late and k == 0) else None) as hook:
                     logits, kl = self.net(x)
                 if not hook.used:
                     self.logits[k].copy_(logits.reshape(self.B, self.C))
