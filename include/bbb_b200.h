@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define BBB_ABI_VERSION 1
+#define BBB_ABI_VERSION 2
 
 enum { BBB_VARIANT_BBB = 0,   /* weight-space sampling   (layers/BBB/...)      */
        BBB_VARIANT_LRT = 1 }; /* local reparameterisation (layers/BBB_LRT/...) */

@@ -116,7 +116,7 @@ def lib():
                         "`python -c 'import __graft_entry__ as g; g.build()'` at the repo root. "
                         "There is no CPU/PyTorch fallback for the Bayesian layer path.")
                 _lib = _bind(C.CDLL(LIB_PATH))
-                if _lib.bbb_abi_version() != 1:
+                if _lib.bbb_abi_version() != 2:
                     raise EngineError("libbbb_b200.so ABI version mismatch")
     return _lib
 

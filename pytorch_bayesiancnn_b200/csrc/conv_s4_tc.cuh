@@ -71,11 +71,16 @@ conv_s4_prep_kernel(const S4Args p) {
     __shared__ double red[32];
     constexpr bool LRT = VARIANT == BBB_VARIANT_LRT;
     const Geom& g = p.g;
-    const NoiseKey nkey = effective_key(p.key, p.stream_base);
     const bool stoch = p.sample != 0, do_kl = p.kl_out != nullptr;
     const int n_items = g.KH * 6 * 64;
     double kl_acc = 0.0;
     tl_enter(p.tl_prep);
+    // launched with programmatic serialization in front of conv_s4_kernel: first make sure OUR predecessor (the step's
+    // noise-advance kernel) is complete -- the conv kernel inherits that guarantee -- then let its CTAs start: they stage
+    // their images while this kernel prepares the weights
+    pdl_wait();
+    pdl_trigger();
+    const NoiseKey nkey = effective_key(p.key, p.stream_base);
     for (int gi = blockIdx.x * blockDim.x + threadIdx.x; gi < n_items; gi += gridDim.x * blockDim.x) {
         const int row = gi & 63, chunk = (gi >> 6) % 6, r = gi / (6 * 64);
         float w[8], s2[8];
@@ -170,12 +175,10 @@ conv_s4_kernel(const S4Args p) {
     }
     const uint32_t tmem_cols = (two && !p.eps_a) ? 512u : (two ? 256u : 128u);      // accumulators (+ the LRT noise tile)
     if (warp == 8) tmem_alloc(smem_u32(&ctl->tmem_base), tmem_cols);
-    pdl_wait();                                                  // everything below reads / writes tensors other kernels touch
-    tl_dep(p.tl_gemm);
-    if (threadIdx.x < 64) {
-        ctl->bias[threadIdx.x] = p.bias_ws[threadIdx.x];
-        ctl->bvar[threadIdx.x] = p.bias_ws[64 + threadIdx.x];
-    }
+    // No CTA-wide griddepcontrol.wait: the programmatic predecessor is this layer's weight-prep kernel (which has itself
+    // waited for everything before it), and staging the images needs nothing it writes.  Only the weight producer (warp 9:
+    // operand tiles, bias) and the workers' noise/epilogue (Philox base, output buffers) wait -- the image staging of all
+    // CTAs overlaps the prep kernel.
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -197,7 +200,7 @@ conv_s4_kernel(const S4Args p) {
         const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(half * 32);
         const uint32_t noise_col = 256u;
         int b_s = b;                                                        // image index inside its MC sample
-        const NoiseKey nkey = fold_key(effective_key(p.key, p.stream_base), p.fold, b, b_s);
+        NoiseKey nkey = p.key;                                              // completed after griddepcontrol.wait (reads the stream base)
         auto noise_slice = [&](int it) {                                    // 16 of this thread's 64 normals: 4 independent Philox chains
             const int ohl = it >> 1, k16 = it & 1;
             float z[16];
@@ -264,8 +267,6 @@ conv_s4_kernel(const S4Args p) {
                     while (lrb >= nb) { lrb -= nb; ++im; }
                 }
                 if (tr && threadIdx.x == 0 && nit < 2) tr[41 + 3 * nit] = clock64();
-                // Philox math while the SECOND batch's loads are in flight (the first batch is what the tensor core waits for)
-                if (philox && batch == 1 && nslice < 1) { noise_slice(nslice); ++nslice; }
                 if (tr && threadIdx.x == 0 && nit < 2) tr[42 + 3 * nit] = clock64();
 #pragma unroll
                 for (int u = 0; u < SB; ++u) {
@@ -287,6 +288,8 @@ conv_s4_kernel(const S4Args p) {
             mbar_arrive(smem_u32(&ctl->img_ready[batch]));
         }
         if (tr && threadIdx.x == 0) tr[2] = clock64();
+        pdl_wait();                                                         // Philox base / output buffers: everything before this launch is complete
+        nkey = fold_key(effective_key(p.key, p.stream_base), p.fold, b, b_s);
         if (philox) {
 #pragma unroll 1
             for (; nslice < 4; ++nslice) noise_slice(nslice);                        // the rest, while the tensor core works
@@ -405,6 +408,13 @@ conv_s4_kernel(const S4Args p) {
         tc_fence_before();
     } else {
         // ================= weight producer ============================================================================
+        pdl_wait();                                                         // the prep kernel's tiles and bias
+        tl_dep(p.tl_gemm, 288);
+        for (int c = lane; c < 64; c += 32) {
+            ctl->bias[c] = p.bias_ws[c];
+            ctl->bvar[c] = p.bias_ws[64 + c];
+        }
+        __syncwarp();                                                       // bias stores ordered before lane 0's first mbarrier arrive
         for (int r = 0; r < g.KH; ++r) {
             const int s = r % S4_STAGES;
             __syncwarp();
@@ -442,9 +452,9 @@ inline cudaError_t launch_conv_s4(S4Args a, cudaStream_t st, bool do_prep, bool 
         }();
         (void)carve;
         const int grid = (g.KH * 6 * 64 + 255) / 256;
-        if (lrt) conv_s4_prep_kernel<BBB_VARIANT_LRT><<<grid, 256, 0, st>>>(a);
-        else     conv_s4_prep_kernel<BBB_VARIANT_BBB><<<grid, 256, 0, st>>>(a);
-        cudaError_t e = cudaGetLastError();
+        cudaError_t e = lrt ? launch_pdl(conv_s4_prep_kernel<BBB_VARIANT_LRT>, dim3(grid), dim3(256), 0, st, a)
+                            : launch_pdl(conv_s4_prep_kernel<BBB_VARIANT_BBB>, dim3(grid), dim3(256), 0, st, a);
+        if (e == cudaSuccess) e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         *n_launch += 1;
     }

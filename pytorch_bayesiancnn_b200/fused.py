@@ -211,7 +211,7 @@ def _run(steps, x, overlap_prep, out, terms, owner, fold=None, after_fork=None):
     The parameter-only half of every layer (softplus / eps / bf16 operand tiles / KL) runs on side
     streams (parallel branches of a captured graph), joined to the GEMM chain by events, so only the
     first layer's prep is on the activation critical path.  The preps are issued in layer order over
-    a few serial chains (default 3: layers 0,3 / 1,4 / 2,5) rather than all at once: six concurrent prep
+    a few serial chains (default 3: layers 1,4 / 2,5 / 3) rather than all at once: six concurrent prep
     grids fill the machine and the first layer's prep -- the one the GEMM chain is waiting for -- was
     scheduled last (measured with tools/timeline.py: first GEMM at 24 us instead of ~20).  The KL sum
     depends on the preps only and runs on the side as well."""
@@ -232,18 +232,31 @@ def _run(steps, x, overlap_prep, out, terms, owner, fold=None, after_fork=None):
             if after_fork is not None:
                 after_fork()
                 after_fork = None
-            events = []
+            # The FIRST layer's prep stays on the main stream, right in front of its GEMM kernel: launched with programmatic
+            # serialization the GEMM kernel's CTAs start while the prep runs and stage their input images meanwhile
+            # (conv_s4_tc.cuh); only its weight producer waits for the prep.  The other preps go to the side chains.
+            events = [None] * len(steps)
+            first_on_main = os.environ.get("BBB_B200_PREP0_MAIN", "1") == "1"
+            ev0 = None
+            if first_on_main:
+                run_step(steps[0], None, None, None, 0, kl=kls[0], noise=noise[0], phase=L.FUSED_PREP_ONLY, fold=fold)
+                ev0 = torch.cuda.Event()
+                ev0.record(main)
             for i, st in enumerate(steps):
-                side = chains[i % len(chains)]
+                if i == 0 and first_on_main:
+                    continue
+                side = chains[(i - 1) % len(chains)] if first_on_main else chains[i % len(chains)]
                 with torch.cuda.stream(side):
                     run_step(st, None, None, None, 0, kl=kls[i], noise=noise[i], phase=L.FUSED_PREP_ONLY, fold=fold)
                     ev = torch.cuda.Event()
                     ev.record(side)
-                    events.append(ev)
+                    events[i] = ev
             for side in chains[1:]:
                 chains[0].wait_stream(side)
             if not terms:
                 with torch.cuda.stream(chains[0]):
+                    if ev0 is not None:
+                        chains[0].wait_event(ev0)
                     kl_total = kls.sum()
         if after_fork is not None:
             after_fork()
@@ -255,7 +268,8 @@ def _run(steps, x, overlap_prep, out, terms, owner, fold=None, after_fork=None):
             nxt = steps[i + 1].layer if i + 1 < len(steps) else None
             y_into = out if (take and i == len(steps) - 1) else None
             if overlap_prep:
-                main.wait_event(events[i])
+                if events[i] is not None:
+                    main.wait_event(events[i])
                 cur, cur_sq, cur_pitch = run_step(st, nxt, cur, cur_sq, cur_pitch, kl=kls[i], noise=noise[i],
                                                   phase=L.FUSED_SKIP_PREP, y_into=y_into, fold=fold)
             else:

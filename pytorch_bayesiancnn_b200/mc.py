@@ -21,6 +21,7 @@ from __future__ import annotations
 import ctypes as C
 from typing import Callable, Optional
 
+import os
 import torch
 
 from . import _lib as L
@@ -190,7 +191,7 @@ class MCForward:
             # base, so for an all-LRT fused chain the kernel is enqueued AFTER the prep streams have forked: the preps
             # start at once instead of behind it.
             adv = (lambda: Fn.noise_advance(base, _STRIDE)) if advance else None
-            late = adv is not None and self._lrt_chain
+            late = adv is not None and self._lrt_chain and os.environ.get("BBB_B200_LATE_ADVANCE", "0") == "1"
             if adv is not None and not late:
                 adv()
             kl_ptr, n_kl = None, 0

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(built):
     from pytorch_bayesiancnn_b200 import _lib
     assert declared == set(_lib.SYMBOLS)
     lib.bbb_abi_version.restype = ctypes.c_int32
-    assert lib.bbb_abi_version() == 1
+    assert lib.bbb_abi_version() == 2
     assert ctypes.sizeof(_lib.LayerDesc) == 4 * 26 + 8
 
 
