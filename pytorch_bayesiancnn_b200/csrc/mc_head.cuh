@@ -85,6 +85,40 @@ mc_exchange_kernel(const McxArgs p) {
     const size_t slot_off = (size_t)(seq & 1u) * p.world * rank_floats;     // in floats, behind the control block
     const float inv_S = 1.0f / (float)p.S_total;
 
+    const float* rx = reinterpret_cast<const float*>(p.peer[p.rank] + MCX_CTRL_BYTES) + slot_off;
+    const bool solo = p.world == 1;     // one rank: the partials never leave the registers (no buffer round trip, no handshake)
+    double nll_acc = 0.0, hit_acc = 0.0;
+    // per-row state of the finish (4): running argmax, entropy, the label's log-probability
+    struct RowFin { float best; int best_c; float ent, lab_lp; long long lab; };
+    auto fin_elem = [&](RowFin& rf, size_t e, int c, float M, float tot, float sp, float sp2, float sl) {
+        const float lo = M + logf(tot * inv_S);                           // utils.py:14-22
+        p.log_outputs[e] = lo;
+        if (lo > rf.best) { rf.best = lo; rf.best_c = c; }
+        if ((long long)c == rf.lab) rf.lab_lp = lo;
+        if (p.want_moments) {
+            const float pbar = sp * inv_S, p2 = sp2 * inv_S;
+            if (p.pred) p.pred[e] = sl * inv_S;                           // uncertainty_estimation.py:82-83
+            if (p.epistemic) p.epistemic[e] = p2 - pbar * pbar;           // :89-91  (E[p^2] - p_bar^2)
+            if (p.aleatoric) p.aleatoric[e] = pbar - p2;                  // :94-95  (p_bar - E[p^2])
+            rf.ent -= pbar > 0.0f ? pbar * logf(pbar) : 0.0f;             // H[p_bar] (no reference)
+        }
+    };
+    // row reductions: entropy, the label's log-probability, argmax (first maximal class, like torch.argmax on ties)
+    auto fin_row = [&](RowFin& rf, int b) {
+        float ent = warp_sum(rf.ent), lab_lp = warp_sum(rf.lab_lp), best = rf.best;
+        int best_c = rf.best_c;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+            if (ob > best || (ob == best && oc < best_c)) { best = ob; best_c = oc; }
+        }
+        if (lane == 0) {
+            if (p.entropy && p.want_moments) p.entropy[b] = ent;
+            if (p.labels) { nll_acc -= (double)lab_lp; hit_acc += (best_c == (int)rf.lab) ? 1.0 : 0.0; }
+        }
+    };
+
     // ---- (1) local partials of this CTA's images, pushed to every rank's receive buffer ---------------------
     for (int b = b0 + warp; b < b1; b += nwarp) {
         for (int s = 0; s < p.S_local; ++s) {                   // row normaliser of every local sample
@@ -106,6 +140,7 @@ mc_exchange_kernel(const McxArgs p) {
             if (lane == 0) norm_s[warp][s] = r;
         }
         __syncwarp();
+        RowFin rf{-INFINITY, 0x7fffffff, 0.0f, 0.0f, (solo && p.labels) ? p.labels[b] : -1};
         for (int c = lane; c < C; c += 32) {
             float mx = -INFINITY, acc = 0.0f, sp = 0.0f, sp2 = 0.0f, sl = 0.0f;
             for (int s = 0; s < p.S_local; ++s) {
@@ -118,22 +153,28 @@ mc_exchange_kernel(const McxArgs p) {
                 sp += pr; sp2 += pr * pr; sl += l;
             }
             const size_t e = (size_t)b * C + c;
+            if (solo) { fin_elem(rf, e, c, mx, acc, sp, sp2, sl); continue; }
             for (int q = 0; q < p.world; ++q) {
                 float* dst = reinterpret_cast<float*>(p.peer[q] + MCX_CTRL_BYTES) + slot_off + (size_t)p.rank * rank_floats;
                 dst[e] = mx; dst[BC + e] = acc;
                 if (p.want_moments) { dst[2 * (size_t)BC + e] = sp; dst[3 * (size_t)BC + e] = sp2; dst[4 * (size_t)BC + e] = sl; }
             }
         }
+        if (solo) fin_row(rf, b);
         __syncwarp();
     }
-    if (blockIdx.x == 0 && threadIdx.x < p.world) {             // this rank's KL contribution: S_local * kl
-        float* dst = reinterpret_cast<float*>(p.peer[threadIdx.x] + MCX_CTRL_BYTES) + slot_off + (size_t)p.rank * rank_floats;
-        float one = 0.0f;
-        for (int i = 0; p.kl && i < p.n_kl; ++i) one += __ldg(p.kl + i);
-        dst[(size_t)mcx_planes(p.want_moments) * BC] = (float)p.S_local * one;
-    }
-    __syncthreads();
-    if (p.world > 1) {
+    float kl_solo = 0.0f;
+    if (solo) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) for (int i = 0; p.kl && i < p.n_kl; ++i) kl_solo += __ldg(p.kl + i);
+        kl_solo *= (float)p.S_local;
+    } else {
+        if (blockIdx.x == 0 && threadIdx.x < p.world) {             // this rank's KL contribution: S_local * kl
+            float* dst = reinterpret_cast<float*>(p.peer[threadIdx.x] + MCX_CTRL_BYTES) + slot_off + (size_t)p.rank * rank_floats;
+            float one = 0.0f;
+            for (int i = 0; p.kl && i < p.n_kl; ++i) one += __ldg(p.kl + i);
+            dst[(size_t)mcx_planes(p.want_moments) * BC] = (float)p.S_local * one;
+        }
+        __syncthreads();
         // ---- (2) publish: everything this CTA stored is visible system-wide before its flags are.  The CTA barrier above
         // orders the other threads' stores before these threads; each of them then fences at system scope and
         // releases its flag on one peer.
@@ -150,51 +191,35 @@ mc_exchange_kernel(const McxArgs p) {
             }
         }
         __syncthreads();
-    }
-    // ---- (4) finish: fixed rank order => bitwise identical on every rank ----------------------------------
-    const float* rx = reinterpret_cast<const float*>(p.peer[p.rank] + MCX_CTRL_BYTES) + slot_off;
-    double nll_acc = 0.0, hit_acc = 0.0;
-    for (int b = b0 + warp; b < b1; b += nwarp) {
-        float best = -INFINITY; int best_c = 0x7fffffff;
-        float ent = 0.0f, lab_lp = 0.0f;
-        const long long lab = p.labels ? p.labels[b] : -1;
-        for (int c = lane; c < C; c += 32) {
-            const size_t e = (size_t)b * C + c;
-            float M = -INFINITY;
-            for (int q = 0; q < p.world; ++q) M = fmaxf(M, __ldcg(rx + (size_t)q * rank_floats + e));
-            float tot = 0.0f, sp = 0.0f, sp2 = 0.0f, sl = 0.0f;
-            for (int q = 0; q < p.world; ++q) {
-                const float* r = rx + (size_t)q * rank_floats;
-                const float mq = __ldcg(r + e), aq = __ldcg(r + BC + e);
-                if (aq > 0.0f) tot += aq * expf(mq - M);
-                if (p.want_moments) { sp += __ldcg(r + 2 * (size_t)BC + e); sp2 += __ldcg(r + 3 * (size_t)BC + e); sl += __ldcg(r + 4 * (size_t)BC + e); }
+        // ---- (4) finish: fixed rank order => bitwise identical on every rank ----------------------------------
+        for (int b = b0 + warp; b < b1; b += nwarp) {
+            RowFin rf{-INFINITY, 0x7fffffff, 0.0f, 0.0f, p.labels ? p.labels[b] : -1};
+            for (int c = lane; c < C; c += 32) {
+                const size_t e = (size_t)b * C + c;
+                float M = -INFINITY;
+                for (int q = 0; q < p.world; ++q) M = fmaxf(M, __ldcg(rx + (size_t)q * rank_floats + e));
+                float tot = 0.0f, sp = 0.0f, sp2 = 0.0f, sl = 0.0f;
+                for (int q = 0; q < p.world; ++q) {
+                    const float* r = rx + (size_t)q * rank_floats;
+                    const float mq = __ldcg(r + e), aq = __ldcg(r + BC + e);
+                    if (aq > 0.0f) tot += aq * expf(mq - M);
+                    if (p.want_moments) { sp += __ldcg(r + 2 * (size_t)BC + e); sp2 += __ldcg(r + 3 * (size_t)BC + e); sl += __ldcg(r + 4 * (size_t)BC + e); }
+                }
+                fin_elem(rf, e, c, M, tot, sp, sp2, sl);
             }
-            const float lo = M + logf(tot * inv_S);                       // utils.py:14-22
-            p.log_outputs[e] = lo;
-            if (lo > best) { best = lo; best_c = c; }
-            if ((long long)c == lab) lab_lp = lo;
-            if (p.want_moments) {
-                const float pbar = sp * inv_S, p2 = sp2 * inv_S;
-                if (p.pred) p.pred[e] = sl * inv_S;                       // uncertainty_estimation.py:82-83
-                if (p.epistemic) p.epistemic[e] = p2 - pbar * pbar;       // :89-91  (E[p^2] - p_bar^2)
-                if (p.aleatoric) p.aleatoric[e] = pbar - p2;              // :94-95  (p_bar - E[p^2])
-                ent -= pbar > 0.0f ? pbar * logf(pbar) : 0.0f;            // H[p_bar] (no reference)
-            }
-        }
-        // row reductions: entropy, the label's log-probability, argmax (first maximal class, like torch.argmax on ties)
-        ent = warp_sum(ent); lab_lp = warp_sum(lab_lp);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-            const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
-            if (ob > best || (ob == best && oc < best_c)) { best = ob; best_c = oc; }
-        }
-        if (lane == 0) {
-            if (p.entropy && p.want_moments) p.entropy[b] = ent;
-            if (p.labels) { nll_acc -= (double)lab_lp; hit_acc += (best_c == (int)lab) ? 1.0 : 0.0; }
+            fin_row(rf, b);
         }
     }
     // ---- (5) cross-CTA finish (deterministic order), KL, ELBO head, sequence number ------------------------
+    if (solo && !(p.head && p.labels)) {
+        // nothing crosses CTAs: KL / Philox base by one thread; the sequence number (slot choice, handshake) is unused
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            if (p.kl_out) *p.kl_out = kl_solo * inv_S;                    // main_bayesian.py:51  (kl / num_ens)
+            if (p.noise_base) *p.noise_base += p.noise_inc;
+        }
+        tl_exit(p.tl);
+        return;
+    }
     const double nll_cta = block_sum(nll_acc, red);
     __syncthreads();
     const double hit_cta = block_sum(hit_acc, red);
@@ -205,7 +230,12 @@ mc_exchange_kernel(const McxArgs p) {
         if (prev == gridDim.x - 1) {
             __threadfence();
             float klsum = 0.0f;
-            for (int q = 0; q < p.world; ++q) klsum += __ldcg(rx + (size_t)q * rank_floats + (size_t)mcx_planes(p.want_moments) * BC);
+            if (solo) {
+                for (int i = 0; p.kl && i < p.n_kl; ++i) klsum += __ldg(p.kl + i);
+                klsum *= (float)p.S_local;
+            } else {
+                for (int q = 0; q < p.world; ++q) klsum += __ldcg(rx + (size_t)q * rank_floats + (size_t)mcx_planes(p.want_moments) * BC);
+            }
             const float kl = klsum * inv_S;                               // main_bayesian.py:51  (kl / num_ens)
             if (p.kl_out) *p.kl_out = kl;
             if (p.head && p.labels) {

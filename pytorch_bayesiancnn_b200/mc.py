@@ -184,26 +184,23 @@ class MCForward:
         from . import fused
         from .graph import _STRIDE
         with torch.no_grad():
-            # The Philox base moves at the HEAD of a captured step.  (Measured: a captured step whose first kernel on the
-            # capture stream carries the programmatic-launch attribute but has no kernel before it loses the programmatic
-            # edges of the whole chain -- every GEMM then starts ~3.5 us after its predecessor ends, 129 vs 113 us per
-            # step; with this one-thread kernel in front the overlap is back.)  LRT weight preps do not read the noise
-            # base, so for an all-LRT fused chain the kernel is enqueued AFTER the prep streams have forked: the preps
-            # start at once instead of behind it.
-            adv = (lambda: Fn.noise_advance(base, _STRIDE)) if advance else None
-            late = adv is not None and self._lrt_chain and os.environ.get("BBB_B200_LATE_ADVANCE", "0") == "1"
-            if adv is not None and not late:
-                adv()
+            # The Philox base moves at the HEAD of a captured step, BEFORE the prep streams fork.  Measured (B200, captured
+            # step, tools/quick_step.py): with this one-thread kernel as the single root of the graph every GEMM kernel of
+            # the chain is launched programmatically behind its predecessor (100 us per step); with the fork in front of it
+            # (prep kernels as further root nodes) or with no plain kernel at the head, the programmatic edges of the whole
+            # chain are lost -- every GEMM then starts ~3 us after its predecessor ends (132 us per step).
+            if advance:
+                Fn.noise_advance(base, _STRIDE)
             kl_ptr, n_kl = None, 0
             if self.fold_steps is not None:
                 with Fn.stream_base(base), Fn.mc_sample(self.ids[0], self.seed):
                     _, kls = fused._run(self.fold_steps, x, True, self.logits.view(len(self.ids) * self.B, self.C), True, None,
-                                        fold=self.fold, after_fork=adv if late else None)
+                                        fold=self.fold)
                 self._kl_terms = kls
                 kl_ptr, n_kl = Fn._ptr(kls), kls.numel()
             for k, j in enumerate(self.ids if self.fold_steps is None else ()):
                 with Fn.stream_base(base), Fn.mc_sample(j, self.seed), \
-                        fused.direct_output(self.logits[k], adv if (late and k == 0) else None) as hook:
+                        fused.direct_output(self.logits[k]) as hook:
                     logits, kl = self.net(x)
                 if not hook.used:
                     self.logits[k].copy_(logits.reshape(self.B, self.C))
