@@ -225,10 +225,13 @@ def run_ours(args):
     # The step = the package's public MC step (mc.MCForward): this rank's samples through the engine (fused tcgen05 chain),
     # then ONE kernel that combines them, exchanges the partials with the other ranks over NVLink and finishes
     # logmeanexp / KL (/ uncertainty) on the device -- all in one captured CUDA graph per resident input batch.
-    eng = mc.MCForward(net, x_dev[0], S_total, want_uncertainty=cfg["uncertainty"], seed=2024, static_inputs=x_dev)
+    # overlap=True: the exchange kernel of step t runs on its own stream beside the first kernels of step t+1 (the windows
+    # below end with eng.wait(), so every timed step's exchange is inside the timed region)
+    ovl = os.environ.get("BBB_B200_MC_OVERLAP", "1") == "1"
+    eng = mc.MCForward(net, x_dev[0], S_total, want_uncertainty=cfg["uncertainty"], seed=2024, static_inputs=x_dev, overlap=ovl)
     staging = [torch.empty_like(x_dev[0]) for _ in range(2)]
     eng_e2e = mc.MCForward(net, x_dev[0], S_total, want_uncertainty=cfg["uncertainty"], seed=2024, static_inputs=staging,
-                           first_replay=1 << 18)
+                           first_replay=1 << 18, overlap=ovl)
     S_local = len(eng.ids)
     main = torch.cuda.current_stream(dev)
 
@@ -258,6 +261,7 @@ def run_ours(args):
         for _ in range(nsteps):
             eng(slot=counter[0] % n_dev_inputs)
             counter[0] += 1
+        eng.wait()
 
     window(resident, args.warmup)
     sampler = ClockSampler(local)
@@ -294,8 +298,11 @@ def run_ours(args):
             main.wait_event(ready[s])
             out = eng_e2e(slot=s)
             consumed[s].record(main)
-            out_host.copy_(out["log_outputs"], non_blocking=True)
-            kl_host.copy_(out["kl"].reshape(1), non_blocking=True)
+            with torch.cuda.stream(eng_e2e.result_stream or main):     # the stream the step's results are complete on
+                out_host.copy_(out["log_outputs"], non_blocking=True)
+                kl_host.copy_(out["kl"].reshape(1), non_blocking=True)
+        if eng_e2e.result_stream is not None:
+            main.wait_stream(eng_e2e.result_stream)
 
     window(e2e_steps, max(3, args.warmup))
     e2e_wins = [window(e2e_steps, args.steps) for _ in range(max(5, args.windows // 3))]

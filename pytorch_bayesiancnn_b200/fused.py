@@ -173,14 +173,14 @@ class direct_output:
     kernel sums them: bbb_mc_exchange), so the Monte-Carlo step has no copy and no aten reduction behind the chain.
     ``.used`` tells whether a fused chain really took the buffer (non-fusable nets ignore the hook)."""
 
-    def __init__(self, out, after_fork=None):
-        """``after_fork``: called once on the main stream right after the parameter-prep side streams have forked and
-        before the first GEMM is enqueued (e.g. the step's noise-advance kernel, which LRT preps do not depend on)."""
-        self.out, self.used, self.after_fork = out, False, after_fork
+    def __init__(self, out, kl_buf=None):
+        """``kl_buf``: optional fp32 device vector the per-layer KL scalars are written to (its first n entries are
+        returned) instead of a tensor allocated by the chain -- a stable address for a kernel captured separately."""
+        self.out, self.used, self.kl_buf = out, False, kl_buf
 
     def __enter__(self):
         self.prev = dict(_direct)
-        _direct.update(out=self.out, terms=True, owner=self, after_fork=self.after_fork)
+        _direct.update(out=self.out, terms=True, owner=self, kl_buf=self.kl_buf)
         return self
 
     def __exit__(self, *exc):
@@ -202,10 +202,10 @@ def _prep_chains():
 
 def run(steps, x: torch.Tensor, overlap_prep: bool = True):
     return _run(steps, x, overlap_prep, _direct.get("out"), _direct.get("terms", False), _direct.get("owner"),
-                after_fork=_direct.get("after_fork"))
+                kls_out=_direct.get("kl_buf"))
 
 
-def _run(steps, x, overlap_prep, out, terms, owner, fold=None, after_fork=None):
+def _run(steps, x, overlap_prep, out, terms, owner, fold=None, kls_out=None):
     """Execute a planned chain.  Returns (network output fp32, summed KL 0-dim tensor).
 
     The parameter-only half of every layer (softplus / eps / bf16 operand tiles / KL) runs on side
@@ -216,7 +216,7 @@ def _run(steps, x, overlap_prep, out, terms, owner, fold=None, after_fork=None):
     scheduled last (measured with tools/timeline.py: first GEMM at 24 us instead of ~20).  The KL sum
     depends on the preps only and runs on the side as well."""
     dev = x.device
-    kls = torch.empty(len(steps), dtype=torch.float32, device=dev)
+    kls = kls_out[:len(steps)] if kls_out is not None else torch.empty(len(steps), dtype=torch.float32, device=dev)
     snap = Fn.noise_snapshot()
     main = torch.cuda.current_stream(dev)
     chains = [_side_stream(dev, c) for c in range(min(_prep_chains(), len(steps)))] if overlap_prep else []
@@ -229,9 +229,6 @@ def _run(steps, x, overlap_prep, out, terms, owner, fold=None, after_fork=None):
             for side in chains:
                 side.wait_stream(main)
             forked = True
-            if after_fork is not None:
-                after_fork()
-                after_fork = None
             # The FIRST layer's prep stays on the main stream, right in front of its GEMM kernel: launched with programmatic
             # serialization the GEMM kernel's CTAs start while the prep runs and stage their input images meanwhile
             # (conv_s4_tc.cuh); only its weight producer waits for the prep.  The other preps go to the side chains.
@@ -258,8 +255,6 @@ def _run(steps, x, overlap_prep, out, terms, owner, fold=None, after_fork=None):
                     if ev0 is not None:
                         chains[0].wait_event(ev0)
                     kl_total = kls.sum()
-        if after_fork is not None:
-            after_fork()
         cur, cur_sq, cur_pitch = x.contiguous().float(), None, 0
         last = steps[-1]
         take = (out is not None and last.out_layout == L.LAYOUT_ROWMAJOR_F32 and out.is_contiguous()

@@ -65,10 +65,14 @@ class MCForward:
     def __init__(self, net, example_x: torch.Tensor, num_ens: int, group=None, want_uncertainty: bool = False,
                  normalized: bool = False, with_labels: bool = False, train_size: float = 1.0, beta: float = 0.0,
                  seed: Optional[int] = None, graph: bool = True, num_classes: Optional[int] = None,
-                 static_inputs=None, first_replay: int = 0, fold: bool = True):
+                 static_inputs=None, first_replay: int = 0, fold: bool = True, overlap: bool = False):
         """``static_inputs``: device tensors the caller fills in place (e.g. targets of its host->device copies, or a
         rotation of resident batches); one graph is captured per tensor and ``self(slot=k)`` runs the step on
-        ``static_inputs[k]`` with no staging copy.  ``first_replay``: index of the first replay's noise block."""
+        ``static_inputs[k]`` with no staging copy.  ``first_replay``: index of the first replay's noise block.
+        ``overlap``: run the exchange kernel of step t on its own stream, beside the first kernels of step t+1 (the
+        layer chain of a step does not depend on the previous step's exchange; logits / KL terms / labels are double
+        buffered).  The returned tensors are then complete on ``result_stream`` -- call ``wait()`` before using them on the
+        current stream (a device synchronize covers it too)."""
         Fn._require_cuda(example_x, "MCForward")
         lib = L.lib()
         self.net, self.group = net, group
@@ -96,9 +100,15 @@ class MCForward:
         assert all(t.is_cuda and t.shape == example_x.shape and t.is_contiguous() for t in self.inputs)
         self.x = self.inputs[0]
         self.first_replay = int(first_replay)
-        self.labels = torch.zeros(B, dtype=torch.int64, device=dev) if with_labels else None
-        self.logits = torch.zeros(max(1, len(self.ids)), B, Cc, **f32)
-        self.kl_one = torch.zeros((), **f32)
+        self.overlap = bool(overlap) and graph
+        nbuf = 2 if self.overlap else 1
+        self.labels_all = torch.zeros(nbuf, B, dtype=torch.int64, device=dev) if with_labels else None
+        self.labels = self.labels_all[0] if with_labels else None
+        self.logits_all = torch.zeros(nbuf, max(1, len(self.ids)), B, Cc, **f32)
+        self.logits = self.logits_all[0]
+        self.kl_one_all = torch.zeros(nbuf, **f32)
+        self.kl_one = self.kl_one_all[0]
+        self.kl_terms_all = torch.zeros(nbuf, 64, **f32)
         self.out = {"log_outputs": torch.empty(B, Cc, **f32), "kl": torch.empty((), **f32)}
         if want_uncertainty:
             for k in ("pred", "epistemic", "aleatoric"):
@@ -132,6 +142,7 @@ class MCForward:
         # an all-LRT net that runs as a fused chain: its weight preps do not depend on the step's noise base
         self._lrt_chain = all_lrt and (self.fold_steps is not None or fused.plan(kids, tuple(example_x.shape)) is not None)
         self.graph, self.graphs = None, []
+        self.result_stream = None                 # overlap mode: the stream the results are complete on
         self.replays = 0
         self.kernels_per_step = None
         if graph:
@@ -178,11 +189,19 @@ class MCForward:
 
     # -- one step ----------------------------------------------------------------------------------------------
     def _step(self, x, base=None, advance=False):
-        """This rank's samples through the engine, then the exchange kernel.  A fused chain writes its logits straight
-        into the sample buffer and hands over its per-layer KL scalars un-summed (fused.direct_output); with
-        ``advance`` the exchange kernel also moves the Philox stream base for the next replay."""
+        """This rank's samples through the engine, then the exchange kernel."""
+        kl_ptr, n_kl = self._chain(x, base, advance)
+        self._exchange(kl_ptr, n_kl)
+        return self.out
+
+    def _chain(self, x, base=None, advance=False, par=0):
+        """This rank's samples through the engine into the sample buffer ``par``.  A fused chain writes its logits
+        straight into it and hands over its per-layer KL scalars un-summed (fused.direct_output).  Returns the (pointer,
+        count) of the floats whose sum is one sample's KL."""
         from . import fused
         from .graph import _STRIDE
+        logits_buf = self.logits_all[par]
+        kl_buf = self.kl_terms_all[par] if self.overlap else None
         with torch.no_grad():
             # The Philox base moves at the HEAD of a captured step, BEFORE the prep streams fork.  Measured (B200, captured
             # step, tools/quick_step.py): with this one-thread kernel as the single root of the graph every GEMM kernel of
@@ -194,35 +213,35 @@ class MCForward:
             kl_ptr, n_kl = None, 0
             if self.fold_steps is not None:
                 with Fn.stream_base(base), Fn.mc_sample(self.ids[0], self.seed):
-                    _, kls = fused._run(self.fold_steps, x, True, self.logits.view(len(self.ids) * self.B, self.C), True, None,
-                                        fold=self.fold)
+                    _, kls = fused._run(self.fold_steps, x, True, logits_buf.view(len(self.ids) * self.B, self.C), True, None,
+                                        fold=self.fold, kls_out=kl_buf)
                 self._kl_terms = kls
                 kl_ptr, n_kl = Fn._ptr(kls), kls.numel()
             for k, j in enumerate(self.ids if self.fold_steps is None else ()):
                 with Fn.stream_base(base), Fn.mc_sample(j, self.seed), \
-                        fused.direct_output(self.logits[k]) as hook:
+                        fused.direct_output(logits_buf[k], kl_buf if k == 0 else None) as hook:
                     logits, kl = self.net(x)
                 if not hook.used:
-                    self.logits[k].copy_(logits.reshape(self.B, self.C))
+                    logits_buf[k].copy_(logits.reshape(self.B, self.C))
                 if k == 0:
                     if hook.used:
                         self._kl_terms = kl                       # per-layer scalars of sample 0 (every sample has the same KL)
                         kl_ptr, n_kl = Fn._ptr(kl), kl.numel()
                     else:
-                        self.kl_one.copy_(torch.as_tensor(kl, dtype=torch.float32, device=self.dev))
-                        kl_ptr, n_kl = Fn._ptr(self.kl_one), 1
+                        one = self.kl_one_all[par:par + 1]
+                        one.copy_(torch.as_tensor(kl, dtype=torch.float32, device=self.dev).reshape(1))
+                        kl_ptr, n_kl = Fn._ptr(one), 1
             if not self.ids and self.rank == 0:
                 raise L.EngineError("MCForward: rank 0 must own a sample")
-            self._exchange(kl_ptr, n_kl)
-        return self.out
+        return kl_ptr, n_kl
 
-    def _exchange(self, kl_ptr, n_kl, advance_base=None):
+    def _exchange(self, kl_ptr, n_kl, advance_base=None, par=0):
         """The one kernel behind the samples: combine + exchange + heads (bbb_mc_exchange)."""
         from .graph import _STRIDE
         o = self.out
         rc = L.lib().bbb_mc_exchange(
-            Fn._ptr(self.logits), len(self.ids), self.num_ens, self.B, self.C, kl_ptr, n_kl, self.flags,
-            Fn._ptr(self.labels), C.c_float(self.train_size), C.c_float(self.beta), self.rank, self.world, self.peers,
+            Fn._ptr(self.logits_all[par]), len(self.ids), self.num_ens, self.B, self.C, kl_ptr, n_kl, self.flags,
+            Fn._ptr(self.labels_all[par] if self.labels_all is not None else None), C.c_float(self.train_size), C.c_float(self.beta), self.rank, self.world, self.peers,
             Fn._ptr(self.state), Fn._ptr(o["log_outputs"]), Fn._ptr(o["kl"]), Fn._ptr(o.get("pred")),
             Fn._ptr(o.get("epistemic")), Fn._ptr(o.get("aleatoric")), Fn._ptr(o.get("entropy")), Fn._ptr(o.get("head")),
             Fn._ptr(advance_base), C.c_uint64(_STRIDE if advance_base is not None else 0), Fn._stream(self.dev))
@@ -241,7 +260,28 @@ class MCForward:
         # GEMM chain on a HIGH-priority stream, parameter preps on the (default-priority) side streams: when both have CTAs
         # pending, the chain's go first -- the preps of later layers no longer keep the first GEMM's CTAs off the SMs
         cap = torch.cuda.Stream(device=dev, priority=-1)
-        for xin in self.inputs:
+        if self.overlap:
+            # two graphs per step: the layer chain (per resident input and buffer parity) and the exchange kernel (per
+            # parity); __call__ replays the second on its own stream so that it runs beside the next step's chain
+            self.chain_graphs, self.exch_graphs = [[], []], []
+            for par in (0, 1):
+                for xin in self.inputs:
+                    g = torch.cuda.CUDAGraph()
+                    n0 = L.launch_count()
+                    with torch.cuda.graph(g, stream=cap):
+                        kl_ptr, n_kl = self._chain(xin, self.base, advance=True, par=par)
+                    n_chain = L.launch_count() - n0
+                    self.chain_graphs[par].append(g)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=cap):
+                    self._exchange(kl_ptr, n_kl, par=par)
+                self.exch_graphs.append(g)
+            self.kernels_per_step = n_chain + 1
+            self.graphs = self.chain_graphs[0]
+            self.result_stream = torch.cuda.Stream(device=dev, priority=-1)
+            self._chain_done = [torch.cuda.Event() for _ in range(2)]
+            self._exch_done = [None, None]
+        for xin in (() if self.overlap else self.inputs):
             g = torch.cuda.CUDAGraph()
             n0 = L.launch_count()
             with torch.cuda.graph(g, stream=cap):
@@ -252,9 +292,29 @@ class MCForward:
         self.base.fill_((self.first_replay - 1) * _STRIDE)
 
     def __call__(self, x: Optional[torch.Tensor] = None, labels: Optional[torch.Tensor] = None, slot: int = 0):
+        if labels is not None and self.labels is None:
+            raise L.EngineError("MCForward was built without with_labels=True")
+        if self.overlap:
+            cur = torch.cuda.current_stream(self.dev)
+            par = self.replays & 1
+            if self._exch_done[par] is not None:          # buffers `par` were last read by the exchange of two steps ago
+                cur.wait_event(self._exch_done[par])
+            if labels is not None:
+                self.labels_all[par].copy_(labels, non_blocking=True)
+            if x is not None:
+                self.inputs[slot].copy_(x, non_blocking=True)
+            self.chain_graphs[par][slot].replay()
+            self._chain_done[par].record(cur)
+            rs = self.result_stream
+            rs.wait_event(self._chain_done[par])
+            with torch.cuda.stream(rs):
+                self.exch_graphs[par].replay()
+                ev = self._exch_done[par] = self._exch_done[par] or torch.cuda.Event()
+                ev.record(rs)
+            self._last = par
+            self.replays += 1
+            return self.out
         if labels is not None:
-            if self.labels is None:
-                raise L.EngineError("MCForward was built without with_labels=True")
             self.labels.copy_(labels, non_blocking=True)
         if self.graph is not None:
             if x is not None:
@@ -263,6 +323,12 @@ class MCForward:
             self.replays += 1
             return self.out
         return self._step(self.inputs[slot] if x is None else x.to(self.dev))
+
+    def wait(self):
+        """Make the current stream wait for the last step's results (a no-op unless built with ``overlap=True``)."""
+        if self.overlap and self.replays and self._exch_done[self._last] is not None:
+            torch.cuda.current_stream(self.dev).wait_event(self._exch_done[self._last])
+        return self.out
 
 
 def _generic_mc_forward(forward_fn: Callable, x: torch.Tensor, num_ens: int, group=None, want_uncertainty: bool = False):

@@ -284,6 +284,30 @@ def test_mc_forward_product_path_single_gpu(dev):
     assert eng.timeouts() == 0 and eng.kernels_per_step is not None
 
 
+def test_mc_forward_overlapped_exchange_equals_serial(dev):
+    """overlap=True (exchange kernel of step t on its own stream beside the chain of step t+1; logits / KL terms / labels
+    double buffered) gives bit-identical results to the serial step, step for step, with no synchronisation between steps."""
+    from pytorch_bayesiancnn_b200 import mc
+    net, _ = _net("alexnet", 10, 3, "lrt", dev, "auto")
+    x = torch.randn(128, 3, 32, 32, device=dev)
+    labs = [torch.randint(0, 10, (128,), device=dev) for _ in range(5)]
+    a = mc.MCForward(net, x, 3, want_uncertainty=True, with_labels=True, train_size=10.0, beta=0.2, seed=3)
+    b = mc.MCForward(net, x, 3, want_uncertainty=True, with_labels=True, train_size=10.0, beta=0.2, seed=3, overlap=True)
+    assert b.overlap and b.result_stream is not None
+    for n in (1, 2, 5):                                                      # compare after 1, 3 and 8 steps in total
+        for i in range(n):
+            oa = a(x, labs[i])
+        for i in range(n):
+            ob = b(x, labs[i])
+        b.wait()
+        ra = {k: v.clone() for k, v in oa.items()}
+        rb = {k: v.clone() for k, v in ob.items()}
+        torch.cuda.synchronize()
+        for k in ra:
+            assert torch.equal(ra[k], rb[k]), (n, k)
+    assert b.timeouts() == 0
+
+
 def test_mc_sample_folding_equals_sample_loop(dev):
     """LRT: S local samples folded into ONE pass of the fused chain (each row drawing from its own sample's Philox
     stream) == S passes, one per sample -- same logits, same combine (what makes C3/C4-style steps 2x faster)."""
@@ -358,6 +382,20 @@ def _mp_worker(rank, world, port, num_ens, out_path):
     assert eng.timeouts() == 0
     res = {k: v.cpu() for k, v in out.items()}
     eng.close()
+    # the same three steps with the exchange of step t overlapped with the chain of step t+1 (double-buffered samples)
+    eng2 = mc.MCForward(net, x, num_ens, want_uncertainty=True, with_labels=True, train_size=50000.0, beta=0.1, seed=77, overlap=True)
+    other = torch.randint(0, 10, (256,), generator=torch.Generator().manual_seed(5)).to(dev)
+    for i in range(3):
+        o2 = eng2(x, labels if i == 2 else other)                   # back to back, no synchronisation in between
+    eng2.wait()
+    torch.cuda.synchronize()
+    for k, v in res.items():
+        assert torch.equal(o2[k].cpu(), v), k
+    for _ in range(40):
+        eng2(x, labels)
+    torch.cuda.synchronize()
+    assert eng2.timeouts() == 0
+    eng2.close()
     # sharded training step (row f1): gradients after ONE all-reduce
     tnet, _ = _net("lenet", 10, 3, "lrt", dev, "fp32")
     xt = torch.rand(64, 3, 32, 32, generator=torch.Generator().manual_seed(3)).to(dev)
