@@ -228,10 +228,11 @@ def run_ours(args):
     # overlap=True: the exchange kernel of step t runs on its own stream beside the first kernels of step t+1 (the windows
     # below end with eng.wait(), so every timed step's exchange is inside the timed region)
     ovl = os.environ.get("BBB_B200_MC_OVERLAP", "1") == "1"
-    eng = mc.MCForward(net, x_dev[0], S_total, want_uncertainty=cfg["uncertainty"], seed=2024, static_inputs=x_dev, overlap=ovl)
+    infl = int(os.environ.get("BBB_B200_MC_INFLIGHT", "1"))
+    eng = mc.MCForward(net, x_dev[0], S_total, want_uncertainty=cfg["uncertainty"], seed=2024, static_inputs=x_dev, overlap=ovl, inflight=infl)
     staging = [torch.empty_like(x_dev[0]) for _ in range(2)]
     eng_e2e = mc.MCForward(net, x_dev[0], S_total, want_uncertainty=cfg["uncertainty"], seed=2024, static_inputs=staging,
-                           first_replay=1 << 18, overlap=ovl)
+                           first_replay=1 << 18, overlap=ovl, inflight=infl)
     S_local = len(eng.ids)
     main = torch.cuda.current_stream(dev)
 
@@ -297,7 +298,10 @@ def run_ours(args):
                     ready[s ^ 1].record(copy_stream)
             main.wait_event(ready[s])
             out = eng_e2e(slot=s)
-            consumed[s].record(main)
+            if eng_e2e.input_consumed() is not None:
+                consumed[s] = eng_e2e.input_consumed()                 # the step's chain runs on the engine's own stream
+            else:
+                consumed[s].record(main)
             with torch.cuda.stream(eng_e2e.result_stream or main):     # the stream the step's results are complete on
                 out_host.copy_(out["log_outputs"], non_blocking=True)
                 kl_host.copy_(out["kl"].reshape(1), non_blocking=True)

@@ -18,6 +18,7 @@ namespace {
 thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
 long long* g_trace = nullptr;      // debug hook (bbb_debug_set_trace)
+long long* g_mcx_trace = nullptr;  // debug hook (bbb_debug_set_mcx_trace): handshake stamps of the exchange kernel
 // debug hook (bbb_debug_set_timeline): launch k of the instrumented kernels writes [first CTA entry, last CTA
 // exit] in %globaltimer ns to g_tl[2k], g_tl[2k+1]; the slot index is fixed at launch (= capture) time
 long long* g_tl = nullptr;
@@ -403,13 +404,14 @@ int bbb_mc_exchange(const float* logits, int32_t S_local, int32_t S_total, int32
     if (const char* e = getenv("BBB_B200_MC_TIMEOUT_MS")) a.timeout_ns = (unsigned long long)atoll(e) * 1000000ull;
     a.head_partials = (double*)((char*)state + 64);
     a.log_outputs = log_outputs; a.kl_out = kl_out; a.pred = pred; a.epistemic = epistemic; a.aleatoric = aleatoric;
-    a.entropy = entropy; a.head = head;
+    a.entropy = entropy; a.head = head; a.trace = g_mcx_trace;
     { bbb::Geom tg = {}; tg.M = B; tg.N = C; tg.K = S_local; a.tl = tl_slot(true, "mc_exchange", tg); }
     // the grid depends on B only: CTA c of every rank owns the same images, so flags pair up CTA by CTA.  At most
     // MCX_MAX_CTAS CTAs: all co-resident, so a CTA spinning on a peer's flag never keeps that peer's producer off an SM.
     int grid = (B + bbb::MCX_THREADS / 32 - 1) / (bbb::MCX_THREADS / 32);
     if (grid > bbb::MCX_MAX_CTAS) grid = bbb::MCX_MAX_CTAS;
-    cudaError_t e = bbb::launch_pdl(bbb::mc_exchange_kernel, dim3(grid), dim3(bbb::MCX_THREADS), 0, (cudaStream_t)cuda_stream, a);
+    cudaError_t e = bbb::launch_pdl(bbb::mc_exchange_kernel, dim3(grid), dim3(bbb::MCX_THREADS),
+                                     (size_t)(bbb::MCX_THREADS / 32) * S_local * sizeof(float), (cudaStream_t)cuda_stream, a);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "mc_exchange launch");
     g_launches += 1;
@@ -462,6 +464,7 @@ int bbb_noise_advance(uint64_t* base, uint64_t inc, void* cuda_stream) {
 
 /* debug only (not in the public header): per-CTA clock64 checkpoints of tap_gemm_kernel */
 void bbb_debug_set_trace(void* dev_ptr) { g_trace = (long long*)dev_ptr; }
+void bbb_debug_set_mcx_trace(void* dev_ptr) { g_mcx_trace = (long long*)dev_ptr; }
 /* debug only: timeline slots (4 x int64 per instrumented launch; caller presets [INT64_MAX, 0, INT64_MAX, 0] before a run) */
 void bbb_debug_set_timeline(void* dev_ptr, int capacity) { g_tl = (long long*)dev_ptr; g_tl_cap = capacity; g_tl_n = 0; }
 int bbb_debug_timeline_count(void) { return g_tl_n; }

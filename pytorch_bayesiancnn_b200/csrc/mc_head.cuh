@@ -15,10 +15,14 @@
 // probability underflows (a plain sum of softmaxes does not).
 //
 // Receive buffer of one rank (all ranks use the same layout):
-//   [0, 4096)                       control: u32 flags[world <= 16][MCX_MAX_CTAS]  (value = sequence number delivered)
-//   [4096, ...)                     float data[2 slots][world][n_planes * B * C + 2]
-// Sequence numbers make the buffer reusable without a reset: launch k of a rank uses slot k & 1 and waits for flag
-// values >= k; a peer can be at most one launch ahead (it cannot finish launch k+1 before it has OUR launch k+1 flags).
+//   [0, 4096)                       reserved
+//   [4096, ...)                     u64 data[2 slots][world][n_planes * B * C + 2]
+// Every float travels as ONE 8-byte store {value bits, sequence number} (the "LL" idea of NCCL's low-latency protocol):
+// 8-byte stores are single-copy atomic over NVLink, so the receiver simply polls each word until its tag equals the
+// launch's sequence number -- no fence, no separate flag, no CTA barrier between the push and the finish.  (Measured
+// with a fence.sys + st.release.sys flag per CTA instead: 3.0 + 3.4 us of fences per step on the critical path.)
+// Tags make the buffer reusable without a reset: launch k of a rank uses slot k & 1; a peer can be at most one launch
+// ahead (it cannot finish launch k+1 before it has OUR launch k+1 words, which we send after we finished reading k).
 #pragma once
 #include "common.cuh"
 
@@ -48,27 +52,32 @@ struct McxArgs {
     float* pred; float* epistemic; float* aleatoric; float* entropy;   // [B,C] x3, [B]; nullable (need want_moments)
     float* head;                  // [4]: loss, nll, accuracy, beta*kl; nullable (needs labels)
     long long* tl;                // debug timeline slot (nullptr in production)
+    long long* trace;             // debug: [CTA][8] %globaltimer stamps of the handshake (nullptr in production)
 };
 
 __host__ __device__ inline int mcx_planes(int want_moments) { return want_moments ? 5 : 2; }
 __host__ __device__ inline size_t mcx_rank_floats(int B, int C, int want_moments) { return (size_t)mcx_planes(want_moments) * B * C + 2; }
 __host__ inline size_t mcx_buffer_bytes(int B, int C, int want_moments, int world) {
-    return MCX_CTRL_BYTES + 2 * (size_t)world * mcx_rank_floats(B, C, want_moments) * sizeof(float);
+    return MCX_CTRL_BYTES + 2 * (size_t)world * mcx_rank_floats(B, C, want_moments) * sizeof(unsigned long long);
 }
 
-__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_ll(unsigned long long* p, float v, unsigned int seq) {
+    const unsigned long long w = ((unsigned long long)seq << 32) | (unsigned long long)__float_as_uint(v);
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
 }
-__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ unsigned long long ld_ll(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ float softplus_f(float v) { return v > 20.0f ? v : log1pf(expf(v)); }   // F.softplus(beta=1, threshold=20)
 
-__global__ void __launch_bounds__(MCX_THREADS)
+// <= 51 registers: an exchange CTA has to fit beside a GEMM CTA (320 x ~120 registers) and a prep CTA of the next step
+__global__ void __launch_bounds__(MCX_THREADS, 5)
 mc_exchange_kernel(const McxArgs p) {
-    __shared__ float norm_s[MCX_THREADS / 32][MCX_MAX_SLOCAL];   // per warp: log-sum-exp (or softplus sum) of each local sample's row
+    // per warp: log-sum-exp (or softplus sum) of each local sample's row -- dynamic, 32 * S_local bytes: next to a 193 KB
+    // GEMM CTA and a 26 KB prep CTA of the NEXT step (overlap mode) a fixed 8 KB array did not fit on the SM any more
+    extern __shared__ float norm_dyn[];
     __shared__ unsigned int seq_sh;
     __shared__ double red[32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = MCX_THREADS / 32;
@@ -78,14 +87,17 @@ mc_exchange_kernel(const McxArgs p) {
     tl_enter(p.tl);
     asm volatile("griddepcontrol.wait;" ::: "memory");      // launched with programmatic serialization: the logits come from the predecessor
     tl_dep(p.tl);
+    const bool tracer = p.trace && threadIdx.x == (p.rank + 1) % p.world;      // the thread that talks to the next rank
+    long long* tr = p.trace + blockIdx.x * 8;
+    if (tracer) tr[0] = (long long)globaltimer_ns();
     if (threadIdx.x == 0) seq_sh = *p.seq + 1u;
     __syncthreads();
     const unsigned int seq = seq_sh;
     const size_t rank_floats = mcx_rank_floats(B, C, p.want_moments);
-    const size_t slot_off = (size_t)(seq & 1u) * p.world * rank_floats;     // in floats, behind the control block
+    const size_t slot_off = (size_t)(seq & 1u) * p.world * rank_floats;     // in words, behind the control block
     const float inv_S = 1.0f / (float)p.S_total;
 
-    const float* rx = reinterpret_cast<const float*>(p.peer[p.rank] + MCX_CTRL_BYTES) + slot_off;
+    const unsigned long long* rx = reinterpret_cast<const unsigned long long*>(p.peer[p.rank] + MCX_CTRL_BYTES) + slot_off;
     const bool solo = p.world == 1;     // one rank: the partials never leave the registers (no buffer round trip, no handshake)
     double nll_acc = 0.0, hit_acc = 0.0;
     // per-row state of the finish (4): running argmax, entropy, the label's log-probability
@@ -119,6 +131,19 @@ mc_exchange_kernel(const McxArgs p) {
         }
     };
 
+    // a word of the receive buffer, once its tag says it belongs to this launch (never hangs: a lost peer = a counted timeout)
+    auto ll_value = [&](unsigned long long v, const unsigned long long* w) -> float {
+        if ((unsigned int)(v >> 32) != seq) {
+            const unsigned long long t0 = globaltimer_ns();
+            unsigned int spins = 0;
+            while ((unsigned int)((v = ld_ll(w)) >> 32) != seq) {
+                __nanosleep(64);          // the SM is shared with the next step's kernels (overlap mode): do not hammer the LSU
+                if ((++spins & 63u) == 0u && globaltimer_ns() - t0 > p.timeout_ns) { atomicAdd(p.timeouts, 1u); break; }
+            }
+        }
+        return __uint_as_float((unsigned int)v);
+    };
+
     // ---- (1) local partials of this CTA's images, pushed to every rank's receive buffer ---------------------
     for (int b = b0 + warp; b < b1; b += nwarp) {
         for (int s = 0; s < p.S_local; ++s) {                   // row normaliser of every local sample
@@ -137,7 +162,7 @@ mc_exchange_kernel(const McxArgs p) {
                 for (int c = lane; c < C; c += 32) se += expf(row[c] - mx);
                 r = mx + logf(warp_sum(se));
             }
-            if (lane == 0) norm_s[warp][s] = r;
+            if (lane == 0) norm_dyn[warp * p.S_local + s] = r;
         }
         __syncwarp();
         RowFin rf{-INFINITY, 0x7fffffff, 0.0f, 0.0f, (solo && p.labels) ? p.labels[b] : -1};
@@ -146,8 +171,8 @@ mc_exchange_kernel(const McxArgs p) {
             for (int s = 0; s < p.S_local; ++s) {
                 const float l = p.logits[((size_t)s * B + b) * C + c];
                 float pr, lp;
-                if (p.normalized) { pr = softplus_f(l) / norm_s[warp][s]; lp = logf(pr); }
-                else { lp = l - norm_s[warp][s]; pr = expf(lp); }            // log_softmax (main_bayesian.py:49)
+                if (p.normalized) { pr = softplus_f(l) / norm_dyn[warp * p.S_local + s]; lp = logf(pr); }
+                else { lp = l - norm_dyn[warp * p.S_local + s]; pr = expf(lp); }            // log_softmax (main_bayesian.py:49)
                 if (lp > mx) { acc = acc * expf(mx - lp) + 1.0f; mx = lp; }  // online logsumexp over the samples
                 else if (lp > -INFINITY) acc += expf(lp - mx);               // lp == -inf: a probability of exactly 0 adds nothing
                 sp += pr; sp2 += pr * pr; sl += l;
@@ -155,9 +180,9 @@ mc_exchange_kernel(const McxArgs p) {
             const size_t e = (size_t)b * C + c;
             if (solo) { fin_elem(rf, e, c, mx, acc, sp, sp2, sl); continue; }
             for (int q = 0; q < p.world; ++q) {
-                float* dst = reinterpret_cast<float*>(p.peer[q] + MCX_CTRL_BYTES) + slot_off + (size_t)p.rank * rank_floats;
-                dst[e] = mx; dst[BC + e] = acc;
-                if (p.want_moments) { dst[2 * (size_t)BC + e] = sp; dst[3 * (size_t)BC + e] = sp2; dst[4 * (size_t)BC + e] = sl; }
+                unsigned long long* dst = reinterpret_cast<unsigned long long*>(p.peer[q] + MCX_CTRL_BYTES) + slot_off + (size_t)p.rank * rank_floats;
+                st_ll(dst + e, mx, seq); st_ll(dst + BC + e, acc, seq);
+                if (p.want_moments) { st_ll(dst + 2 * (size_t)BC + e, sp, seq); st_ll(dst + 3 * (size_t)BC + e, sp2, seq); st_ll(dst + 4 * (size_t)BC + e, sl, seq); }
             }
         }
         if (solo) fin_row(rf, b);
@@ -169,42 +194,53 @@ mc_exchange_kernel(const McxArgs p) {
         kl_solo *= (float)p.S_local;
     } else {
         if (blockIdx.x == 0 && threadIdx.x < p.world) {             // this rank's KL contribution: S_local * kl
-            float* dst = reinterpret_cast<float*>(p.peer[threadIdx.x] + MCX_CTRL_BYTES) + slot_off + (size_t)p.rank * rank_floats;
+            unsigned long long* dst = reinterpret_cast<unsigned long long*>(p.peer[threadIdx.x] + MCX_CTRL_BYTES) + slot_off + (size_t)p.rank * rank_floats;
             float one = 0.0f;
             for (int i = 0; p.kl && i < p.n_kl; ++i) one += __ldg(p.kl + i);
-            dst[(size_t)mcx_planes(p.want_moments) * BC] = (float)p.S_local * one;
+            st_ll(dst + (size_t)mcx_planes(p.want_moments) * BC, (float)p.S_local * one, seq);
         }
-        __syncthreads();
-        // ---- (2) publish: everything this CTA stored is visible system-wide before its flags are.  The CTA barrier above
-        // orders the other threads' stores before these threads; each of them then fences at system scope and
-        // releases its flag on one peer.
-        if (threadIdx.x < p.world) {
-            __threadfence_system();
-            unsigned int* flags = reinterpret_cast<unsigned int*>(p.peer[threadIdx.x]);
-            st_release_sys(flags + p.rank * MCX_MAX_CTAS + blockIdx.x, seq);
-            // ---- (3) wait for the same CTA of that peer -------------------------------------------------------
-            const unsigned int* f = reinterpret_cast<const unsigned int*>(p.peer[p.rank]) + threadIdx.x * MCX_MAX_CTAS + blockIdx.x;
-            const unsigned long long t0 = globaltimer_ns();
-            while ((int)(ld_acquire_sys(f) - seq) < 0) {
-                __nanosleep(20);
-                if (globaltimer_ns() - t0 > p.timeout_ns) { atomicAdd(p.timeouts, 1u); break; }   // never hang the GPU on a lost peer
-            }
-        }
-        __syncthreads();
+        if (tracer) tr[1] = (long long)globaltimer_ns();
         // ---- (4) finish: fixed rank order => bitwise identical on every rank ----------------------------------
         for (int b = b0 + warp; b < b1; b += nwarp) {
             RowFin rf{-INFINITY, 0x7fffffff, 0.0f, 0.0f, p.labels ? p.labels[b] : -1};
             for (int c = lane; c < C; c += 32) {
                 const size_t e = (size_t)b * C + c;
-                float M = -INFINITY;
-                for (int q = 0; q < p.world; ++q) M = fmaxf(M, __ldcg(rx + (size_t)q * rank_floats + e));
-                float tot = 0.0f, sp = 0.0f, sp2 = 0.0f, sl = 0.0f;
-                for (int q = 0; q < p.world; ++q) {
-                    const float* r = rx + (size_t)q * rank_floats;
-                    const float mq = __ldcg(r + e), aq = __ldcg(r + BC + e);
-                    if (aq > 0.0f) tot += aq * expf(mq - M);
-                    if (p.want_moments) { sp += __ldcg(r + 2 * (size_t)BC + e); sp2 += __ldcg(r + 3 * (size_t)BC + e); sl += __ldcg(r + 4 * (size_t)BC + e); }
+                // the words of this element from up to 8 ranks in flight at once (one L2 round trip), stragglers polled;
+                // ranks merged in ascending order with the online logsumexp update: same operations on every rank
+                float M = -INFINITY, tot = 0.0f, mom[3] = {0.0f, 0.0f, 0.0f};
+                for (int q0 = 0; q0 < p.world; q0 += 8) {
+                    unsigned long long wm[8], wa[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (q0 + j >= p.world) continue;
+                        const unsigned long long* r = rx + (size_t)(q0 + j) * rank_floats + e;
+                        wm[j] = ld_ll(r); wa[j] = ld_ll(r + BC);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (q0 + j >= p.world) continue;
+                        const unsigned long long* r = rx + (size_t)(q0 + j) * rank_floats + e;
+                        const float mq = ll_value(wm[j], r), aq = ll_value(wa[j], r + BC);
+                        if (aq > 0.0f) {
+                            if (mq > M) { tot = tot * expf(M - mq) + aq; M = mq; }
+                            else tot += aq * expf(mq - M);
+                        }
+                    }
                 }
+                if (p.want_moments) {
+#pragma unroll
+                    for (int pl = 0; pl < 3; ++pl)
+                        for (int q0 = 0; q0 < p.world; q0 += 8) {
+                            unsigned long long w[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                if (q0 + j < p.world) w[j] = ld_ll(rx + (size_t)(q0 + j) * rank_floats + (size_t)(2 + pl) * BC + e);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                if (q0 + j < p.world) mom[pl] += ll_value(w[j], rx + (size_t)(q0 + j) * rank_floats + (size_t)(2 + pl) * BC + e);
+                        }
+                }
+                const float sp = mom[0], sp2 = mom[1], sl = mom[2];
                 fin_elem(rf, e, c, M, tot, sp, sp2, sl);
             }
             fin_row(rf, b);
@@ -220,21 +256,28 @@ mc_exchange_kernel(const McxArgs p) {
         tl_exit(p.tl);
         return;
     }
-    const double nll_cta = block_sum(nll_acc, red);
-    __syncthreads();
-    const double hit_cta = block_sum(hit_acc, red);
+    if (tracer) tr[5] = (long long)globaltimer_ns();
+    const bool want_head = p.head && p.labels;
+    double nll_cta = 0.0, hit_cta = 0.0;
+    if (want_head) {
+        nll_cta = block_sum(nll_acc, red);
+        __syncthreads();
+        hit_cta = block_sum(hit_acc, red);
+    } else {
+        __syncthreads();                 // the last CTA's bookkeeping below must follow every thread's reads of this launch's slot
+    }
     if (threadIdx.x == 0) {
-        p.head_partials[2 * blockIdx.x] = nll_cta; p.head_partials[2 * blockIdx.x + 1] = hit_cta;
-        __threadfence();
+        // (a fence here also waits for the acknowledgements of this CTA's NVLink stores, ~3 us: only where something is published)
+        if (want_head) { p.head_partials[2 * blockIdx.x] = nll_cta; p.head_partials[2 * blockIdx.x + 1] = hit_cta; __threadfence(); }
         const unsigned int prev = atomicAdd(p.done, 1u);
         if (prev == gridDim.x - 1) {
-            __threadfence();
+            if (want_head) __threadfence();
             float klsum = 0.0f;
             if (solo) {
                 for (int i = 0; p.kl && i < p.n_kl; ++i) klsum += __ldg(p.kl + i);
                 klsum *= (float)p.S_local;
             } else {
-                for (int q = 0; q < p.world; ++q) klsum += __ldcg(rx + (size_t)q * rank_floats + (size_t)mcx_planes(p.want_moments) * BC);
+                for (int q = 0; q < p.world; ++q) { const unsigned long long* w = rx + (size_t)q * rank_floats + (size_t)mcx_planes(p.want_moments) * BC; klsum += ll_value(ld_ll(w), w); }
             }
             const float kl = klsum * inv_S;                               // main_bayesian.py:51  (kl / num_ens)
             if (p.kl_out) *p.kl_out = kl;

@@ -197,6 +197,10 @@ _ws_layer = weakref.WeakKeyDictionary()           # layer-private scratch: modul
 _ws_slot = 0
 
 
+def current_workspace_slot() -> int:
+    return _ws_slot
+
+
 @contextlib.contextmanager
 def workspace_slot(k: int):
     """Layer workspaces (prepared operand tiles, KL partials and counters) are private per (layer, slot).

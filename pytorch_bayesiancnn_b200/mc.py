@@ -65,14 +65,17 @@ class MCForward:
     def __init__(self, net, example_x: torch.Tensor, num_ens: int, group=None, want_uncertainty: bool = False,
                  normalized: bool = False, with_labels: bool = False, train_size: float = 1.0, beta: float = 0.0,
                  seed: Optional[int] = None, graph: bool = True, num_classes: Optional[int] = None,
-                 static_inputs=None, first_replay: int = 0, fold: bool = True, overlap: bool = False):
+                 static_inputs=None, first_replay: int = 0, fold: bool = True, overlap: bool = False, inflight: int = 1):
         """``static_inputs``: device tensors the caller fills in place (e.g. targets of its host->device copies, or a
         rotation of resident batches); one graph is captured per tensor and ``self(slot=k)`` runs the step on
         ``static_inputs[k]`` with no staging copy.  ``first_replay``: index of the first replay's noise block.
         ``overlap``: run the exchange kernel of step t on its own stream, beside the first kernels of step t+1 (the
         layer chain of a step does not depend on the previous step's exchange; logits / KL terms / labels are double
         buffered).  The returned tensors are then complete on ``result_stream`` -- call ``wait()`` before using them on the
-        current stream (a device synchronize covers it too)."""
+        current stream (a device synchronize covers it too).  ``inflight=2`` (with ``overlap``): consecutive steps are
+        independent, so even and odd steps run on two streams with their own layer workspaces and Philox counters -- the
+        head of step t+1 (parameter preps, first layers) fills the SMs the tail of step t leaves idle.  Results are
+        identical to the serial engine; ``wait()`` also covers the inputs (they may be rewritten afterwards)."""
         Fn._require_cuda(example_x, "MCForward")
         lib = L.lib()
         self.net, self.group = net, group
@@ -101,6 +104,7 @@ class MCForward:
         self.x = self.inputs[0]
         self.first_replay = int(first_replay)
         self.overlap = bool(overlap) and graph
+        self.inflight = 2 if (self.overlap and int(inflight) >= 2) else 1
         nbuf = 2 if self.overlap else 1
         self.labels_all = torch.zeros(nbuf, B, dtype=torch.int64, device=dev) if with_labels else None
         self.labels = self.labels_all[0] if with_labels else None
@@ -202,14 +206,15 @@ class MCForward:
         from .graph import _STRIDE
         logits_buf = self.logits_all[par]
         kl_buf = self.kl_terms_all[par] if self.overlap else None
-        with torch.no_grad():
+        inc = _STRIDE * self.inflight
+        with torch.no_grad(), Fn.workspace_slot(par if self.inflight == 2 else Fn.current_workspace_slot()):
             # The Philox base moves at the HEAD of a captured step, BEFORE the prep streams fork.  Measured (B200, captured
             # step, tools/quick_step.py): with this one-thread kernel as the single root of the graph every GEMM kernel of
             # the chain is launched programmatically behind its predecessor (100 us per step); with the fork in front of it
             # (prep kernels as further root nodes) or with no plain kernel at the head, the programmatic edges of the whole
             # chain are lost -- every GEMM then starts ~3 us after its predecessor ends (132 us per step).
             if advance:
-                Fn.noise_advance(base, _STRIDE)
+                Fn.noise_advance(base, inc)
             kl_ptr, n_kl = None, 0
             if self.fold_steps is not None:
                 with Fn.stream_base(base), Fn.mc_sample(self.ids[0], self.seed):
@@ -255,6 +260,8 @@ class MCForward:
         with torch.cuda.stream(side):
             for _ in range(warmup):                 # eager: creates plans / workspaces; every rank runs the same exchanges
                 self._step(self.x, self.base)
+            if self.inflight == 2:                  # the odd steps' own layer workspaces
+                self._exchange(*self._chain(self.x, self.base, par=1), par=1)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         # GEMM chain on a HIGH-priority stream, parameter preps on the (default-priority) side streams: when both have CTAs
@@ -264,12 +271,14 @@ class MCForward:
             # two graphs per step: the layer chain (per resident input and buffer parity) and the exchange kernel (per
             # parity); __call__ replays the second on its own stream so that it runs beside the next step's chain
             self.chain_graphs, self.exch_graphs = [[], []], []
+            self.base2 = torch.zeros(2, dtype=torch.int64, device=dev)
+            self._bases = [self.base2[0:1], self.base2[1:2]] if self.inflight == 2 else [self.base, self.base]
             for par in (0, 1):
                 for xin in self.inputs:
                     g = torch.cuda.CUDAGraph()
                     n0 = L.launch_count()
                     with torch.cuda.graph(g, stream=cap):
-                        kl_ptr, n_kl = self._chain(xin, self.base, advance=True, par=par)
+                        kl_ptr, n_kl = self._chain(xin, self._bases[par], advance=True, par=par)
                     n_chain = L.launch_count() - n0
                     self.chain_graphs[par].append(g)
                 g = torch.cuda.CUDAGraph()
@@ -278,9 +287,16 @@ class MCForward:
                 self.exch_graphs.append(g)
             self.kernels_per_step = n_chain + 1
             self.graphs = self.chain_graphs[0]
-            self.result_stream = torch.cuda.Stream(device=dev, priority=-1)
+            # the exchange kernel is tiny and latency-critical (peers wait for it): highest priority the device offers
+            lo = getattr(torch.cuda.Stream, "priority_range", lambda: (-1, 0))()
+            self.result_stream = torch.cuda.Stream(device=dev, priority=min(lo))
             self._chain_done = [torch.cuda.Event() for _ in range(2)]
             self._exch_done = [None, None]
+            self._in_ready = [torch.cuda.Event() for _ in range(2)]
+            self.chain_streams = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(2)] if self.inflight == 2 else None
+            # replay r draws noise block first_replay + r: with two counters, parity p starts two blocks back and moves by two
+            for p_ in range(2):
+                self.base2[p_] = (self.first_replay + p_ - 2) * _STRIDE
         for xin in (() if self.overlap else self.inputs):
             g = torch.cuda.CUDAGraph()
             n0 = L.launch_count()
@@ -297,14 +313,20 @@ class MCForward:
         if self.overlap:
             cur = torch.cuda.current_stream(self.dev)
             par = self.replays & 1
+            run = cur
+            if self.inflight == 2:                        # even / odd steps on their own streams, behind the caller's work so far
+                run = self.chain_streams[par]
+                self._in_ready[par].record(cur)
+                run.wait_event(self._in_ready[par])
             if self._exch_done[par] is not None:          # buffers `par` were last read by the exchange of two steps ago
-                cur.wait_event(self._exch_done[par])
-            if labels is not None:
-                self.labels_all[par].copy_(labels, non_blocking=True)
-            if x is not None:
-                self.inputs[slot].copy_(x, non_blocking=True)
-            self.chain_graphs[par][slot].replay()
-            self._chain_done[par].record(cur)
+                run.wait_event(self._exch_done[par])
+            with torch.cuda.stream(run):
+                if labels is not None:
+                    self.labels_all[par].copy_(labels, non_blocking=True)
+                if x is not None:
+                    self.inputs[slot].copy_(x, non_blocking=True)
+                self.chain_graphs[par][slot].replay()
+                self._chain_done[par].record(run)
             rs = self.result_stream
             rs.wait_event(self._chain_done[par])
             with torch.cuda.stream(rs):
@@ -327,8 +349,14 @@ class MCForward:
     def wait(self):
         """Make the current stream wait for the last step's results (a no-op unless built with ``overlap=True``)."""
         if self.overlap and self.replays and self._exch_done[self._last] is not None:
+            # exchanges run in step order on one stream and each follows its chain: the last one covers everything before
             torch.cuda.current_stream(self.dev).wait_event(self._exch_done[self._last])
         return self.out
+
+    def input_consumed(self):
+        """Event after which the input of the LAST step may be rewritten (its layer chain has read it); None = stream order
+        of the current stream already says so."""
+        return self._chain_done[self._last] if (self.overlap and self.replays) else None
 
 
 def _generic_mc_forward(forward_fn: Callable, x: torch.Tensor, num_ens: int, group=None, want_uncertainty: bool = False):

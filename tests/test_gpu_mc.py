@@ -293,19 +293,22 @@ def test_mc_forward_overlapped_exchange_equals_serial(dev):
     labs = [torch.randint(0, 10, (128,), device=dev) for _ in range(5)]
     a = mc.MCForward(net, x, 3, want_uncertainty=True, with_labels=True, train_size=10.0, beta=0.2, seed=3)
     b = mc.MCForward(net, x, 3, want_uncertainty=True, with_labels=True, train_size=10.0, beta=0.2, seed=3, overlap=True)
-    assert b.overlap and b.result_stream is not None
+    # inflight=2: even / odd steps on two streams with their own layer workspaces and Philox counters
+    c = mc.MCForward(net, x, 3, want_uncertainty=True, with_labels=True, train_size=10.0, beta=0.2, seed=3, overlap=True, inflight=2)
+    assert b.overlap and b.result_stream is not None and c.inflight == 2
     for n in (1, 2, 5):                                                      # compare after 1, 3 and 8 steps in total
         for i in range(n):
             oa = a(x, labs[i])
-        for i in range(n):
-            ob = b(x, labs[i])
-        b.wait()
         ra = {k: v.clone() for k, v in oa.items()}
-        rb = {k: v.clone() for k, v in ob.items()}
-        torch.cuda.synchronize()
-        for k in ra:
-            assert torch.equal(ra[k], rb[k]), (n, k)
-    assert b.timeouts() == 0
+        for eng in (b, c):
+            for i in range(n):
+                ob = eng(x, labs[i])
+            eng.wait()
+            rb = {k: v.clone() for k, v in ob.items()}
+            torch.cuda.synchronize()
+            for k in ra:
+                assert torch.equal(ra[k], rb[k]), (n, k, eng.inflight)
+    assert b.timeouts() == 0 and c.timeouts() == 0
 
 
 def test_mc_sample_folding_equals_sample_loop(dev):
@@ -396,6 +399,19 @@ def _mp_worker(rank, world, port, num_ens, out_path):
     torch.cuda.synchronize()
     assert eng2.timeouts() == 0
     eng2.close()
+    eng3 = mc.MCForward(net, x, num_ens, want_uncertainty=True, with_labels=True, train_size=50000.0, beta=0.1, seed=77, overlap=True,
+                        inflight=2)
+    for i in range(3):
+        o3 = eng3(x, labels if i == 2 else other)
+    eng3.wait()
+    torch.cuda.synchronize()
+    for k, v in res.items():
+        assert torch.equal(o3[k].cpu(), v), ("inflight2", k)
+    for _ in range(40):
+        eng3(x, labels)
+    torch.cuda.synchronize()
+    assert eng3.timeouts() == 0
+    eng3.close()
     # sharded training step (row f1): gradients after ONE all-reduce
     tnet, _ = _net("lenet", 10, 3, "lrt", dev, "fp32")
     xt = torch.rand(64, 3, 32, 32, generator=torch.Generator().manual_seed(3)).to(dev)

@@ -17,7 +17,8 @@ dev = torch.device("cuda:0")
 net = build_net(variant, 10, dev, "bf16")
 xs = [torch.randn(B, 3, 32, 32, device=dev) for _ in range(24)]   # 24 x 6 MB: inputs never L2-warm
 bbb.manual_seed(1)
-eng = mc.MCForward(net, xs[0], S, seed=1, static_inputs=xs, overlap=os.environ.get("BBB_B200_MC_OVERLAP", "0") == "1")
+eng = mc.MCForward(net, xs[0], S, seed=1, static_inputs=xs, overlap=os.environ.get("BBB_B200_MC_OVERLAP", "0") == "1",
+                   inflight=int(os.environ.get("BBB_B200_MC_INFLIGHT", "1")))
 for k in range(10):
     eng(slot=k % 24)
 win = []
