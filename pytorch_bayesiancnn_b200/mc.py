@@ -72,8 +72,8 @@ class MCForward:
         ``overlap``: run the exchange kernel of step t on its own stream, beside the first kernels of step t+1 (the
         layer chain of a step does not depend on the previous step's exchange; logits / KL terms / labels are double
         buffered).  The returned tensors are then complete on ``result_stream`` -- call ``wait()`` before using them on the
-        current stream (a device synchronize covers it too).  ``inflight=2`` (with ``overlap``): consecutive steps are
-        independent, so even and odd steps run on two streams with their own layer workspaces and Philox counters -- the
+        current stream (a device synchronize covers it too).  ``inflight=k`` (with ``overlap``): consecutive steps are
+        independent, so steps t, t+1, .. t+k-1 run on k streams with their own layer workspaces and Philox counters -- the
         head of step t+1 (parameter preps, first layers) fills the SMs the tail of step t leaves idle.  Results are
         identical to the serial engine; ``wait()`` also covers the inputs (they may be rewritten afterwards)."""
         Fn._require_cuda(example_x, "MCForward")
@@ -104,8 +104,9 @@ class MCForward:
         self.x = self.inputs[0]
         self.first_replay = int(first_replay)
         self.overlap = bool(overlap) and graph
-        self.inflight = 2 if (self.overlap and int(inflight) >= 2) else 1
-        nbuf = 2 if self.overlap else 1
+        self.inflight = max(1, min(int(inflight), 8)) if self.overlap else 1
+        self.nbuf = max(2, self.inflight) if self.overlap else 1
+        nbuf = self.nbuf
         self.labels_all = torch.zeros(nbuf, B, dtype=torch.int64, device=dev) if with_labels else None
         self.labels = self.labels_all[0] if with_labels else None
         self.logits_all = torch.zeros(nbuf, max(1, len(self.ids)), B, Cc, **f32)
@@ -207,7 +208,7 @@ class MCForward:
         logits_buf = self.logits_all[par]
         kl_buf = self.kl_terms_all[par] if self.overlap else None
         inc = _STRIDE * self.inflight
-        with torch.no_grad(), Fn.workspace_slot(par if self.inflight == 2 else Fn.current_workspace_slot()):
+        with torch.no_grad(), Fn.workspace_slot(par if self.inflight > 1 else Fn.current_workspace_slot()):
             # The Philox base moves at the HEAD of a captured step, BEFORE the prep streams fork.  Measured (B200, captured
             # step, tools/quick_step.py): with this one-thread kernel as the single root of the graph every GEMM kernel of
             # the chain is launched programmatically behind its predecessor (100 us per step); with the fork in front of it
@@ -260,8 +261,8 @@ class MCForward:
         with torch.cuda.stream(side):
             for _ in range(warmup):                 # eager: creates plans / workspaces; every rank runs the same exchanges
                 self._step(self.x, self.base)
-            if self.inflight == 2:                  # the odd steps' own layer workspaces
-                self._exchange(*self._chain(self.x, self.base, par=1), par=1)
+            for p_ in range(1, self.inflight):      # the other in-flight steps' own layer workspaces
+                self._exchange(*self._chain(self.x, self.base, par=p_), par=p_)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         # GEMM chain on a HIGH-priority stream, parameter preps on the (default-priority) side streams: when both have CTAs
@@ -270,10 +271,11 @@ class MCForward:
         if self.overlap:
             # two graphs per step: the layer chain (per resident input and buffer parity) and the exchange kernel (per
             # parity); __call__ replays the second on its own stream so that it runs beside the next step's chain
-            self.chain_graphs, self.exch_graphs = [[], []], []
-            self.base2 = torch.zeros(2, dtype=torch.int64, device=dev)
-            self._bases = [self.base2[0:1], self.base2[1:2]] if self.inflight == 2 else [self.base, self.base]
-            for par in (0, 1):
+            nb = self.nbuf
+            self.chain_graphs, self.exch_graphs = [[] for _ in range(nb)], []
+            self.base2 = torch.zeros(nb, dtype=torch.int64, device=dev)
+            self._bases = [self.base2[p_:p_ + 1] for p_ in range(nb)] if self.inflight > 1 else [self.base] * nb
+            for par in range(nb):
                 for xin in self.inputs:
                     g = torch.cuda.CUDAGraph()
                     n0 = L.launch_count()
@@ -290,13 +292,13 @@ class MCForward:
             # the exchange kernel is tiny and latency-critical (peers wait for it): highest priority the device offers
             lo = getattr(torch.cuda.Stream, "priority_range", lambda: (-1, 0))()
             self.result_stream = torch.cuda.Stream(device=dev, priority=min(lo))
-            self._chain_done = [torch.cuda.Event() for _ in range(2)]
-            self._exch_done = [None, None]
-            self._in_ready = [torch.cuda.Event() for _ in range(2)]
-            self.chain_streams = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(2)] if self.inflight == 2 else None
-            # replay r draws noise block first_replay + r: with two counters, parity p starts two blocks back and moves by two
-            for p_ in range(2):
-                self.base2[p_] = (self.first_replay + p_ - 2) * _STRIDE
+            self._chain_done = [torch.cuda.Event() for _ in range(nb)]
+            self._exch_done = [None] * nb
+            self._in_ready = [torch.cuda.Event() for _ in range(nb)]
+            self.chain_streams = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(nb)] if self.inflight > 1 else None
+            # replay r draws noise block first_replay + r: with k counters, counter p starts k blocks back and moves by k
+            for p_ in range(nb):
+                self.base2[p_] = (self.first_replay + p_ - nb) * _STRIDE
         for xin in (() if self.overlap else self.inputs):
             g = torch.cuda.CUDAGraph()
             n0 = L.launch_count()
@@ -312,9 +314,9 @@ class MCForward:
             raise L.EngineError("MCForward was built without with_labels=True")
         if self.overlap:
             cur = torch.cuda.current_stream(self.dev)
-            par = self.replays & 1
+            par = self.replays % self.nbuf
             run = cur
-            if self.inflight == 2:                        # even / odd steps on their own streams, behind the caller's work so far
+            if self.inflight > 1:                        # even / odd steps on their own streams, behind the caller's work so far
                 run = self.chain_streams[par]
                 self._in_ready[par].record(cur)
                 run.wait_event(self._in_ready[par])

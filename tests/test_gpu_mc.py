@@ -295,12 +295,13 @@ def test_mc_forward_overlapped_exchange_equals_serial(dev):
     b = mc.MCForward(net, x, 3, want_uncertainty=True, with_labels=True, train_size=10.0, beta=0.2, seed=3, overlap=True)
     # inflight=2: even / odd steps on two streams with their own layer workspaces and Philox counters
     c = mc.MCForward(net, x, 3, want_uncertainty=True, with_labels=True, train_size=10.0, beta=0.2, seed=3, overlap=True, inflight=2)
-    assert b.overlap and b.result_stream is not None and c.inflight == 2
+    d = mc.MCForward(net, x, 3, want_uncertainty=True, with_labels=True, train_size=10.0, beta=0.2, seed=3, overlap=True, inflight=3)
+    assert b.overlap and b.result_stream is not None and c.inflight == 2 and d.inflight == 3
     for n in (1, 2, 5):                                                      # compare after 1, 3 and 8 steps in total
         for i in range(n):
             oa = a(x, labs[i])
         ra = {k: v.clone() for k, v in oa.items()}
-        for eng in (b, c):
+        for eng in (b, c, d):
             for i in range(n):
                 ob = eng(x, labs[i])
             eng.wait()
@@ -308,7 +309,7 @@ def test_mc_forward_overlapped_exchange_equals_serial(dev):
             torch.cuda.synchronize()
             for k in ra:
                 assert torch.equal(ra[k], rb[k]), (n, k, eng.inflight)
-    assert b.timeouts() == 0 and c.timeouts() == 0
+    assert b.timeouts() == 0 and c.timeouts() == 0 and d.timeouts() == 0
 
 
 def test_mc_sample_folding_equals_sample_loop(dev):
