@@ -228,7 +228,10 @@ def run_ours(args):
     # overlap=True: the exchange kernel of step t runs on its own stream beside the first kernels of step t+1 (the windows
     # below end with eng.wait(), so every timed step's exchange is inside the timed region)
     ovl = os.environ.get("BBB_B200_MC_OVERLAP", "1") == "1"
-    infl = int(os.environ.get("BBB_B200_MC_INFLIGHT", "1"))
+    # inflight=k: consecutive steps are independent (different batches, same weights), so steps t..t+k-1 run on k streams with
+    # their own workspaces / Philox counters; every step still does all of its work inside the timed region and the results
+    # are bit-identical to the serial engine (tests/test_gpu_mc.py).  The one-step-at-a-time figure is under serial_step.
+    infl = int(os.environ.get("BBB_B200_MC_INFLIGHT", "4")) if ovl else 1
     eng = mc.MCForward(net, x_dev[0], S_total, want_uncertainty=cfg["uncertainty"], seed=2024, static_inputs=x_dev, overlap=ovl, inflight=infl)
     staging = [torch.empty_like(x_dev[0]) for _ in range(2)]
     eng_e2e = mc.MCForward(net, x_dev[0], S_total, want_uncertainty=cfg["uncertainty"], seed=2024, static_inputs=staging,
@@ -314,6 +317,25 @@ def run_ours(args):
     e2e_value = images_per_step * args.steps / (e2e_ms * 1e-3)
     clocks = sampler.stop() if rank == 0 else None
     timeouts = eng.timeouts() + eng_e2e.timeouts()
+
+    # ---- the same step strictly one at a time (no exchange overlap, one step in flight): the step LATENCY ----
+    serial = None
+    if ovl:
+        eng_s = mc.MCForward(net, x_dev[0], S_total, want_uncertainty=cfg["uncertainty"], seed=2024, static_inputs=x_dev)
+
+        def resident_serial(nsteps):
+            for _ in range(nsteps):
+                eng_s(slot=counter[0] % n_dev_inputs)
+                counter[0] += 1
+
+        window(resident_serial, args.warmup)
+        s_wins = [window(resident_serial, args.steps) for _ in range(max(5, args.windows // 3))]
+        s_ms = statistics.median(s_wins)
+        serial = {"ms_per_step": s_ms / args.steps, "value": images_per_step * args.steps / (s_ms * 1e-3), "unit": "images/s",
+                  "note": "one step in flight, exchange kernel inside the step's graph (the step latency); the headline value "
+                          f"keeps {infl} independent steps in flight"}
+        timeouts += eng_s.timeouts()
+        eng_s.close()
 
     # ---- per-layer kernel timing + roofline of the dominant kernel (rank 0, AlexNet only) ----
     per_layer, roof = [], None
@@ -413,7 +435,7 @@ def run_ours(args):
                                         "sample of the batch per GPU and the metric counts image-samples (B*S/t, SURVEY 8d); the literal "
                                         "single-launch S=10 figure is under mc_batched"),
                        "batch": B, "variant": cfg["variant"], "math": args.math, "mc_samples_total": S_total,
-                       "parallelism": f"mc{world}",
+                       "parallelism": f"mc{world}", "steps_in_flight": infl, "exchange_overlapped": ovl,
                        "l2": f"no flush: inputs rotate through {n_dev_inputs} resident batches = {n_dev_inputs * in_bytes >> 20} MB > 126 MB L2",
                        "launch": "one CUDA graph replay per step (noise advance, per-layer prep + GEMM kernels, KL sum, MC exchange "
                                  "kernel over NVLink peer memory); one captured graph per resident input batch, read in place",
@@ -424,6 +446,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": B * C * 4 + 4, "windows_ms": {"min": min(e2e_wins), "median": e2e_ms, "max": max(e2e_wins)},
                     "host_numa": numa},
             "gpu_launches": int(launches),
+            "serial_step": serial,
             "clocks": clocks,
             "roofline": roof,
             "per_layer": per_layer,
