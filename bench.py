@@ -186,6 +186,10 @@ def run_ours(args):
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torch.distributed.run for --gpus > 1")
     numa = pin_to_gpu_numa_node(local)
+    # The GPU arms do no CPU math: keep the OpenMP pool at one thread, as torch.distributed.run does for N > 1.  Measured
+    # (tools/e2e_probe.py, profiles/r2_e2e_probe.txt): with 64 idle-spinning OpenMP workers the pinned H2D path dropped from
+    # 53.5 to 17-26 GB/s and the N=1 end-to-end figure was half of one rank's at N=2.  The CPU baseline leg sets its own count.
+    torch.set_num_threads(1)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist = None
