@@ -728,7 +728,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--variant", default="lrt", choices=["lrt", "bbb"])
-    ap.add_argument("--math", default=os.environ.get("BBB_B200_MATH", "bf16"), choices=["fp32", "bf16", "auto"])
+    ap.add_argument("--math", default=os.environ.get("BBB_B200_MATH", "bf16"), choices=["fp32", "bf16", "tf32", "auto"])
     ap.add_argument("--batch", type=int, default=512)
     ap.add_argument("--classes", type=int, default=10)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)

@@ -40,7 +40,9 @@ enum { BBB_VARIANT_BBB = 0,   /* weight-space sampling   (layers/BBB/...)      *
 enum { BBB_DTYPE_F32 = 0, BBB_DTYPE_BF16 = 1 };
 enum { BBB_MATH_FP32 = 0,      /* CUDA-core FFMA, IEEE fp32 accumulate          */
        BBB_MATH_BF16_TC = 1,   /* tcgen05 bf16 x bf16 -> fp32 in TMEM           */
-       BBB_MATH_AUTO = 2 };    /* engine picks per layer shape                  */
+       BBB_MATH_AUTO = 2,      /* engine picks per layer shape                  */
+       BBB_MATH_TF32_TC = 3 }; /* tcgen05 tf32 x tf32 -> fp32 in TMEM (operands rounded to tf32, 10-bit mantissa: what the
+                                  reference's own GPU conv computes by default); per-layer calls only */
 enum { BBB_KL_REFERENCE = 0,   /* as executed by the reference: KL(prior||post) */
        BBB_KL_TEXTBOOK = 1 };  /* KL(q||p)                                      */
 enum { BBB_ACT_NONE = 0, BBB_ACT_SOFTPLUS = 1, BBB_ACT_RELU = 2 };

@@ -15,13 +15,13 @@ LIB_PATH = os.path.join(_HERE, "libbbb_b200.so")
 
 VARIANT_BBB, VARIANT_LRT = 0, 1
 DTYPE_F32, DTYPE_BF16 = 0, 1
-MATH_FP32, MATH_BF16_TC, MATH_AUTO = 0, 1, 2
+MATH_FP32, MATH_BF16_TC, MATH_AUTO, MATH_TF32_TC = 0, 1, 2, 3
 KL_REFERENCE, KL_TEXTBOOK = 0, 1
 ACT_NONE, ACT_SOFTPLUS, ACT_RELU = 0, 1, 2
 LAYOUT_NCHW_F32, LAYOUT_PACKED_BF16, LAYOUT_ROWMAJOR_F32 = 0, 1, 2
 FUSED_PREP_ONLY, FUSED_SKIP_PREP = 1, 2
 
-MATH_BY_NAME = {"fp32": MATH_FP32, "bf16": MATH_BF16_TC, "auto": MATH_AUTO}
+MATH_BY_NAME = {"fp32": MATH_FP32, "bf16": MATH_BF16_TC, "auto": MATH_AUTO, "tf32": MATH_TF32_TC}
 KL_BY_NAME = {"reference": KL_REFERENCE, "textbook": KL_TEXTBOOK}
 ACT_BY_NAME = {None: ACT_NONE, "none": ACT_NONE, "softplus": ACT_SOFTPLUS, "relu": ACT_RELU}
 

@@ -78,13 +78,15 @@ int forward_impl(const bbb_layer_desc* d, bool linear, const void* x, const floa
 
     int math = d->math;
     if (math == BBB_MATH_AUTO) math = bbb::tc_supported(*d, g) ? BBB_MATH_BF16_TC : BBB_MATH_FP32;
-    if (math == BBB_MATH_BF16_TC) {
-        if (!bbb::tc_supported(*d, g)) return fail(BBB_E_UNSUPPORTED, "BBB_MATH_BF16_TC: shape not supported by the tcgen05 path");
+    if (math == BBB_MATH_BF16_TC || math == BBB_MATH_TF32_TC) {
+        if (!bbb::tc_supported(*d, g)) return fail(BBB_E_UNSUPPORTED, "tcgen05 math mode: shape not supported by the tcgen05 path");
         const size_t need = kTcOffset + bbb::tc_workspace_bytes(g);
         if (!ws || ws_bytes < need) return fail(BBB_E_WORKSPACE, "workspace too small for the tcgen05 path: need %zu bytes", need);
         bbb::TcArgs a;
         a.wtiles = (__nv_bfloat16*)((char*)ws + kTcOffset);
-        a.bias_ws = (float*)((char*)ws + kTcOffset + (size_t)bbb::tc_npad(g) * bbb::tc_kpad(g) * 4);
+        a.tf32 = math == BBB_MATH_TF32_TC;
+        // operand tiles: 2 planes x npad rows x (kpad * 2 bytes of bf16 | kpad32 * 4 bytes of tf32), then the bias rows
+        a.bias_ws = (float*)((char*)ws + kTcOffset + (size_t)bbb::tc_npad(g) * bbb::tc_kpad(g, a.tf32) * (a.tf32 ? 8 : 4));
         a.skip_prep = 0; a.prep_only = 0; a.y_sq = nullptr; a.out_mode = 2; a.out_pitch = 0; a.pool = 0; a.trace = g_trace;
         a.tl_prep = tl_slot(true, "weight_prep", g); a.tl_gemm = tl_slot(true, "gemm_tc", g);
         a.g = g; a.x = x; a.w_mu = W_mu; a.w_rho = W_rho; a.b_mu = bias_mu; a.b_rho = bias_rho;
@@ -201,7 +203,7 @@ int bbb_linear_backward(const bbb_layer_desc* desc, const void* x, const void* g
 static int fused_check(const bbb_layer_desc* d, bbb::Geom& g, int32_t in_layout, int32_t in_pitch, int32_t prev_hw,
                        int32_t out_layout, int32_t out_pitch) {
     if (int rc = check_desc(d, g, false)) return rc;
-    if (d->math == BBB_MATH_FP32) return fail(BBB_E_UNSUPPORTED, "the fused chain exists on the tcgen05 (bf16) path only");
+    if (d->math == BBB_MATH_FP32 || d->math == BBB_MATH_TF32_TC) return fail(BBB_E_UNSUPPORTED, "the fused chain exists on the tcgen05 (bf16) path only");
     const int pool = d->pool_k != 0;
     if (pool && !(d->pool_k == 2 && d->pool_s == 2)) return fail(BBB_E_UNSUPPORTED, "only a 2x2 stride-2 max-pool can be fused");
     if (pool && ((g.OH | g.OW) & 1)) return fail(BBB_E_UNSUPPORTED, "fused pool needs even output height/width");
@@ -283,6 +285,7 @@ int bbb_layer_forward_fused(const bbb_layer_desc* d, const void* x, const void* 
         a.act_dtype = d->act_dtype; a.variant = d->variant;
         a.wtiles = (__nv_bfloat16*)((char*)ws + kTcOffset);
         a.bias_ws = (float*)((char*)ws + kTcOffset + (size_t)bbb::tc_npad(g) * bbb::tc_kpad(g) * 4);
+        a.tf32 = 0;
         a.trace = g_trace; a.skip_prep = skip_prep; a.prep_only = prep_only; a.y_sq = y_sq; a.out_mode = out_mode == 1 ? 2 : out_mode; a.out_pitch = out_pitch; a.pool = pool;
         a.tl_prep = tl_slot(!skip_prep, "weight_prep", g); a.tl_gemm = tl_slot(!prep_only, "gemm_tc", g);
         cudaError_t e = bbb::launch_fwd_tc(a, st, sm_count(), &nl);

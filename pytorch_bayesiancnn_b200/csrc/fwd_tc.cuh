@@ -44,10 +44,11 @@ struct TcArgs {
     float prior_mu, prior_sigma;
     int sample, kl_convention, has_bias, act, act_dtype, variant;
     // prepared-operand workspace
-    __nv_bfloat16* wtiles;   // [n_tiles][k_blocks][planes][64*64]
+    __nv_bfloat16* wtiles;   // [n_tiles][k_blocks][planes][8 KB tile]  (64 rows x 8 K chunks of 16 bytes: 64 bf16 or 32 tf32 of K)
     float* bias_ws;          // [2][Npad]: row 0 = bias (BBB: sampled; LRT: mu), row 1 = LRT sigma_b^2
     int n_tiles, k_blocks, planes;
     int skip_prep, prep_only;
+    int tf32;                // operands as tf32 (fp32 storage, 4 elements per 16-byte K chunk, kind::tf32) instead of bf16
     int stage_x;             // stage the tile's input images in shared memory: 0 no, 1 as fp32, 2 as bf16 (half the
                              // footprint: lets two LRT CTAs share an SM; x^2 is then formed from the bf16 value)
     // fused epilogue (first layer of a fused chain): 2x2 max-pool + packed bf16 output
@@ -64,7 +65,9 @@ constexpr int TC_SMEM_LIMIT = 227 * 1024;
 
 inline int tc_planes(int variant, int sample) { return (variant == BBB_VARIANT_LRT && sample) ? 2 : 1; }
 inline size_t tc_stage_bytes(int planes) { return (size_t)planes * (TC_A_BYTES + TC_B_BYTES); }
-inline int tc_kpad(const Geom& g) { return (g.K + TC_BK - 1) / TC_BK * TC_BK; }
+// A K block is 8 chunks of 16 bytes per row whatever the operand type: 64 bf16 or 32 tf32 elements of K.
+__host__ __device__ constexpr int tc_bk(bool tf32) { return tf32 ? TC_BK / 2 : TC_BK; }
+inline int tc_kpad(const Geom& g, bool tf32 = false) { return (g.K + tc_bk(tf32) - 1) / tc_bk(tf32) * tc_bk(tf32); }
 inline int tc_npad(const Geom& g) { return (g.N + TC_BN - 1) / TC_BN * TC_BN; }
 inline size_t tc_fixed_smem(const Geom& g) { return 2048 /*two 1 KB alignment slacks*/ + 1024 /*barriers + bias*/ + (size_t)tc_kpad(g) * 8; }
 inline int tc_stages(const Geom& g, int planes) {
@@ -74,13 +77,14 @@ inline int tc_stages(const Geom& g, int planes) {
     return (int)s;
 }
 inline size_t tc_workspace_bytes(const Geom& g) {
-    return (size_t)tc_npad(g) * tc_kpad(g) * 2 /*planes*/ * 2 /*bf16*/ + (size_t)2 * tc_npad(g) * 4;
+    // 2 planes of operand tiles (bf16: kpad * 2 bytes per row, tf32: kpad32 * 4 -- never less) + bias rows
+    return (size_t)tc_npad(g) * tc_kpad(g, true) * 2 /*planes*/ * 4 /*tf32*/ + (size_t)2 * tc_npad(g) * 4;
 }
 inline bool tc_supported(const bbb_layer_desc& d, const Geom& g) {
     if (d.act_dtype != BBB_DTYPE_F32) return false;
     if (g.M < 1 || g.N < 1) return false;
     if (tc_stages(g, 2) < 2) return false;
-    if ((long)tc_npad(g) / TC_BN * (tc_kpad(g) / TC_BK) > 1 << 20) return false;
+    if ((long)tc_npad(g) / TC_BN * (tc_kpad(g, true) / tc_bk(true)) > 1 << 20) return false;
     if (tc_npad(g) / TC_BN > 65535) return false;      // n tiles ride on gridDim.y
     return true;
 }
@@ -126,6 +130,15 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], tf32 x tf32 -> fp32 (operands: fp32 words, the low 13 mantissa bits ignored)
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -186,6 +199,26 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 // N>>3 at [17,23), M>>4 at [24,29).
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// kind::tf32: a/b_format = TF32 (2)
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// round-to-nearest tf32 (10-bit mantissa) kept in an fp32 word: the tensor core would otherwise truncate
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return u;
+}
+// one 16-byte K chunk of an operand row: 8 bf16 or 4 tf32 values
+template <bool TF32>
+__device__ __forceinline__ uint4 pack_chunk(const float (&v)[8]) {
+    if (TF32) return make_uint4(to_tf32(v[0]), to_tf32(v[1]), to_tf32(v[2]), to_tf32(v[3]));
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    const __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+    return make_uint4(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b),
+                      *reinterpret_cast<const uint32_t*>(&c), *reinterpret_cast<const uint32_t*>(&d));
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -277,11 +310,12 @@ __device__ __noinline__ void store_row16(const StoreCfg p, int b, int pos, int n
 // ------------------------------------------------------------ (P) weight prep
 // One CTA per (n-tile, k-block) 64x64 tile (grid-stride).  256 threads: item = (row, 8-wide
 // K chunk); consecutive threads take consecutive rows so the 16-byte writes are contiguous.
-template <int VARIANT>
+template <int VARIANT, bool TF32>
 __global__ void __launch_bounds__(256)
 weight_prep_kernel(const TcArgs p) {
     __shared__ double red[32];
     constexpr bool LRT = VARIANT == BBB_VARIANT_LRT;
+    constexpr int CE = TF32 ? 4 : 8, BKE = 8 * CE;                  // elements per 16-byte chunk / per K block
     const Geom& g = p.g;
     const NoiseKey nkey = effective_key(p.key, p.stream_base);
     const bool stoch = p.sample != 0;
@@ -294,12 +328,12 @@ weight_prep_kernel(const TcArgs p) {
     for (long gi = (long)blockIdx.x * blockDim.x + threadIdx.x; gi < n_items; gi += (long)gridDim.x * blockDim.x) {
         const int tile = (int)(gi / PER_TILE), item = (int)(gi - (long)tile * PER_TILE);
         const int nt = tile / p.k_blocks, kb = tile - nt * p.k_blocks;
-        __nv_bfloat16* dst = p.wtiles + (size_t)tile * p.planes * TC_TILE_ELEMS;
+        uint8_t* dst = reinterpret_cast<uint8_t*>(p.wtiles) + (size_t)tile * p.planes * TC_B_BYTES;
         const int row = item & (TC_BN - 1), chunk = item >> 6;
-        const int n = nt * TC_BN + row, k0 = kb * TC_BK + chunk * 8;
-        float w[8], s2[8];
+        const int n = nt * TC_BN + row, k0 = kb * BKE + chunk * CE;
+        float w[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, s2[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
+        for (int e = 0; e < CE; ++e) {
             const int k = k0 + e;
             float wv = 0.0f, sv = 0.0f;
             if (n < g.N && k < g.K) {
@@ -317,12 +351,8 @@ weight_prep_kernel(const TcArgs p) {
             w[e] = wv; s2[e] = sv;
         }
         // canonical K-major core-matrix order inside the 8 KB tile: chunk*1024 + row*16 bytes
-        uint4 o = make_uint4(pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]), pack_bf16(w[4], w[5]), pack_bf16(w[6], w[7]));
-        *reinterpret_cast<uint4*>(dst + chunk * (TC_BN * 8) + row * 8) = o;
-        if (p.planes == 2) {
-            uint4 o2 = make_uint4(pack_bf16(s2[0], s2[1]), pack_bf16(s2[2], s2[3]), pack_bf16(s2[4], s2[5]), pack_bf16(s2[6], s2[7]));
-            *reinterpret_cast<uint4*>(dst + TC_TILE_ELEMS + chunk * (TC_BN * 8) + row * 8) = o2;
-        }
+        *reinterpret_cast<uint4*>(dst + chunk * (TC_BN * 16) + row * 16) = pack_chunk<TF32>(w);
+        if (p.planes == 2) *reinterpret_cast<uint4*>(dst + TC_B_BYTES + chunk * (TC_BN * 16) + row * 16) = pack_chunk<TF32>(s2);
     }
     for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < npad; n += gridDim.x * blockDim.x) {   // bias
         float bm = 0.0f, bv = 0.0f;
@@ -359,10 +389,11 @@ __host__ __device__ inline int tc_tile_images(int OHW) {
     return OHW >= TC_BM ? 2 : (TC_BM + OHW - 1) / OHW + 1;
 }
 
-template <int VARIANT>
+template <int VARIANT, bool TF32>
 __global__ void __launch_bounds__(320, 2)
 gemm_tc_kernel(const TcArgs p, const int stages) {
     constexpr bool LRT = VARIANT == BBB_VARIANT_LRT;
+    constexpr int CE = TF32 ? 4 : 8, BKE = 8 * CE;                  // elements per 16-byte chunk / per K block
     extern __shared__ uint8_t smem_raw[];
     const Geom& g = p.g;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -374,7 +405,7 @@ gemm_tc_kernel(const TcArgs p, const int stages) {
     uint8_t* sm = smem_raw + (base - raw);
     TcSmem* ctl = reinterpret_cast<TcSmem*>(sm);
     int2* ktab = reinterpret_cast<int2*>(sm + 1024);
-    const int kpad = p.k_blocks * TC_BK;
+    const int kpad = p.k_blocks * BKE;
     const uint32_t tiles_off = (1024u + (uint32_t)kpad * 8u + 1023u) & ~1023u;
     const uint32_t stage_bytes = (uint32_t)planes * (TC_A_BYTES + TC_B_BYTES);
     // stage layout: [A (16K)] [A^2 (16K, LRT)] [B planes (8K each)]
@@ -478,22 +509,21 @@ gemm_tc_kernel(const TcArgs p, const int stages) {
             uint8_t* st = sm + tiles_off + (size_t)s * stage_bytes;
 #pragma unroll 2
             for (int c8 = half * 4; c8 < half * 4 + 4; ++c8) {
-                float v[8];
+                float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const int2 kt = ktab[kb * TC_BK + c8 * 8 + e];
+                for (int e = 0; e < CE; ++e) {
+                    const int2 kt = ktab[kb * BKE + c8 * CE + e];
                     const int ih = ih0 + (kt.y >> 16), iw = iw0 + (kt.y & 0xffff);
                     float val = 0.0f;
                     if (mvalid && (unsigned)ih < (unsigned)g.H && (unsigned)iw < (unsigned)g.W)
                         val = (p.stage_x == 2) ? __bfloat162float(xsh[xb + kt.x]) : xp[xb + kt.x];
                     v[e] = val;
                 }
-                const uint4 o = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-                *reinterpret_cast<uint4*>(st + a_off + c8 * (TC_BM * 16) + t * 16) = o;
+                *reinterpret_cast<uint4*>(st + a_off + c8 * (TC_BM * 16) + t * 16) = pack_chunk<TF32>(v);
                 if (two) {
-                    const uint4 o2 = make_uint4(pack_bf16(v[0] * v[0], v[1] * v[1]), pack_bf16(v[2] * v[2], v[3] * v[3]),
-                                                pack_bf16(v[4] * v[4], v[5] * v[5]), pack_bf16(v[6] * v[6], v[7] * v[7]));
-                    *reinterpret_cast<uint4*>(st + a2_off + c8 * (TC_BM * 16) + t * 16) = o2;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[e] *= v[e];
+                    *reinterpret_cast<uint4*>(st + a2_off + c8 * (TC_BM * 16) + t * 16) = pack_chunk<TF32>(v);
                 }
             }
             fence_proxy_async();                        // generic-proxy stores -> visible to the tensor core
@@ -576,7 +606,8 @@ gemm_tc_kernel(const TcArgs p, const int stages) {
         tc_fence_before();
     } else if (warp == 8) {
         // ================= MMA issuer ==========================================
-        constexpr uint32_t idesc = make_idesc_bf16(TC_BM, TC_BN);
+        // one MMA = two 16-byte K chunks per row (K = 16 bf16 or 8 tf32): the byte geometry is the same for both types
+        constexpr uint32_t idesc = TF32 ? make_idesc_tf32(TC_BM, TC_BN) : make_idesc_bf16(TC_BM, TC_BN);
         for (int kb = 0; kb < p.k_blocks; ++kb) {
             const int s = kb % stages;
             const uint32_t ph = (uint32_t)(kb / stages) & 1u;
@@ -586,14 +617,16 @@ gemm_tc_kernel(const TcArgs p, const int stages) {
             if (lane == 0) {
                 const uint32_t st = base + tiles_off + (uint32_t)s * stage_bytes;
 #pragma unroll
-                for (int j = 0; j < TC_BK / 16; ++j) {
+                for (int j = 0; j < 4; ++j) {
                     const uint64_t da = make_smem_desc(st + a_off + j * 2 * (TC_BM * 16), TC_BM * 16, 128);
                     const uint64_t db = make_smem_desc(st + b_off + j * 2 * (TC_BN * 16), TC_BN * 16, 128);
-                    umma_bf16(tmem, da, db, idesc, (kb | j) ? 1u : 0u);
+                    if (TF32) umma_tf32(tmem, da, db, idesc, (kb | j) ? 1u : 0u);
+                    else umma_bf16(tmem, da, db, idesc, (kb | j) ? 1u : 0u);
                     if (two) {
                         const uint64_t da2 = make_smem_desc(st + a2_off + j * 2 * (TC_BM * 16), TC_BM * 16, 128);
                         const uint64_t db2 = make_smem_desc(st + b_off + TC_B_BYTES + j * 2 * (TC_BN * 16), TC_BN * 16, 128);
-                        umma_bf16(tmem + 64u, da2, db2, idesc, (kb | j) ? 1u : 0u);
+                        if (TF32) umma_tf32(tmem + 64u, da2, db2, idesc, (kb | j) ? 1u : 0u);
+                        else umma_bf16(tmem + 64u, da2, db2, idesc, (kb | j) ? 1u : 0u);
                     }
                 }
                 umma_commit(smem_u32(&ctl->empty[s]));            // frees the smem stage when the MMAs retire
@@ -607,7 +640,7 @@ gemm_tc_kernel(const TcArgs p, const int stages) {
         // whole warp waits (a blocking try_wait with one active lane is woken ~750 cycles late), lane 0 issues
         {
             const uint32_t bytes = (uint32_t)planes * TC_B_BYTES;
-            const __nv_bfloat16* src0 = p.wtiles + (size_t)n_tile * p.k_blocks * planes * TC_TILE_ELEMS;
+            const uint8_t* src0 = reinterpret_cast<const uint8_t*>(p.wtiles) + (size_t)n_tile * p.k_blocks * planes * TC_B_BYTES;
             for (int kb = 0; kb < p.k_blocks; ++kb) {
                 const int s = kb % stages;
                 const uint32_t ph = (uint32_t)(kb / stages) & 1u;
@@ -616,7 +649,7 @@ gemm_tc_kernel(const TcArgs p, const int stages) {
                 if (lane == 0) {
                     const uint32_t bar = smem_u32(&ctl->full[s]);
                     mbar_arrive_expect_tx(bar, bytes);
-                    bulk_g2s(base + tiles_off + (uint32_t)s * stage_bytes + b_off, src0 + (size_t)kb * planes * TC_TILE_ELEMS, bytes, bar);
+                    bulk_g2s(base + tiles_off + (uint32_t)s * stage_bytes + b_off, src0 + (size_t)kb * planes * TC_B_BYTES, bytes, bar);
                 }
                 __syncwarp();
             }
@@ -629,15 +662,11 @@ gemm_tc_kernel(const TcArgs p, const int stages) {
     tl_exit(p.tl_gemm, 256);
 }
 
-inline cudaError_t launch_fwd_tc(TcArgs a, cudaStream_t st, int n_sm, int* n_launch) {
+template <int VARIANT, bool TF32>
+inline cudaError_t launch_fwd_tc_t(TcArgs a, cudaStream_t st, int* n_launch) {
     const Geom& g = a.g;
-    a.planes = tc_planes(a.variant, a.sample);
-    a.n_tiles = tc_npad(g) / TC_BN;
-    a.k_blocks = tc_kpad(g) / TC_BK;
-    *n_launch = 0;
-    const bool lrt = a.variant == BBB_VARIANT_LRT;
     if (!a.skip_prep) {
-        const long items = (long)a.n_tiles * a.k_blocks * TC_BN * (TC_BK / 8);
+        const long items = (long)a.n_tiles * a.k_blocks * TC_BN * 8;
         int grid = (int)((items + 255) / 256);
         if (grid > 2048) grid = 2048;
         // Same shared-memory carve-out as the GEMM kernels: an SM only changes its L1/smem split when idle, so prep
@@ -646,13 +675,11 @@ inline cudaError_t launch_fwd_tc(TcArgs a, cudaStream_t st, int n_sm, int* n_lau
         static const bool carve = [] {
             const char* e = getenv("BBB_B200_PREP_CARVEOUT");
             if (e && e[0] == '0') return false;
-            cudaFuncSetAttribute(weight_prep_kernel<BBB_VARIANT_LRT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            cudaFuncSetAttribute(weight_prep_kernel<BBB_VARIANT_BBB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(weight_prep_kernel<VARIANT, TF32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             return true;
         }();
         (void)carve;
-        if (lrt) weight_prep_kernel<BBB_VARIANT_LRT><<<grid, 256, 0, st>>>(a);
-        else     weight_prep_kernel<BBB_VARIANT_BBB><<<grid, 256, 0, st>>>(a);
+        weight_prep_kernel<VARIANT, TF32><<<grid, 256, 0, st>>>(a);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         *n_launch += 1;
@@ -664,36 +691,40 @@ inline cudaError_t launch_fwd_tc(TcArgs a, cudaStream_t st, int n_sm, int* n_lau
     // SM (2 x (2 x 48 KB) for LRT), which hides the gather latency of one CTA behind the other and halves the waves
     if (a.k_blocks <= 8 && stages > 2) stages = 2;
     // exact footprint: base-alignment slack + control/k-table (rounded to 1 KB) + ring (+ staged images)
-    const size_t tiles_off = (1024 + (size_t)tc_kpad(g) * 8 + 1023) / 1024 * 1024;
+    const size_t tiles_off = (1024 + (size_t)tc_kpad(g, TF32) * 8 + 1023) / 1024 * 1024;
     size_t smem = 1023 + tiles_off + (size_t)stages * tc_stage_bytes(a.planes);
     const size_t xs_elems = (size_t)tc_tile_images(g.OHW) * g.Cin * g.HW;
     a.stage_x = 0;
     if (xs_elems * 4 <= 32 * 1024 && smem + xs_elems * 4 <= (size_t)TC_SMEM_LIMIT) {
         a.stage_x = 1;
         // two CTAs per SM need 2 * (smem + 1 KB reserved) <= 228 KB: try the half-size bf16 staging when fp32 does not fit
+        // (never for tf32 operands: the staged copy would already have lost the bits tf32 keeps)
         const size_t per_sm = 228 * 1024;
-        if (2 * (smem + xs_elems * 4 + 1024) > per_sm && 2 * ((smem + xs_elems * 2 + 127) / 128 * 128 + 1024) <= per_sm) a.stage_x = 2;
+        if (!TF32 && 2 * (smem + xs_elems * 4 + 1024) > per_sm && 2 * ((smem + xs_elems * 2 + 127) / 128 * 128 + 1024) <= per_sm) a.stage_x = 2;
         smem += xs_elems * (a.stage_x == 2 ? 2 : 4);
     }
     dim3 grid((g.M + TC_BM - 1) / TC_BM, a.n_tiles);
-    cudaError_t e;
-    if (lrt) {
-        cudaFuncSetAttribute(gemm_tc_kernel<BBB_VARIANT_LRT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        e = cudaFuncSetAttribute(gemm_tc_kernel<BBB_VARIANT_LRT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        e = launch_pdl(gemm_tc_kernel<BBB_VARIANT_LRT>, grid, dim3(320), smem, st, a, stages);
-        if (e != cudaSuccess) return e;
-    } else {
-        cudaFuncSetAttribute(gemm_tc_kernel<BBB_VARIANT_BBB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        e = cudaFuncSetAttribute(gemm_tc_kernel<BBB_VARIANT_BBB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        e = launch_pdl(gemm_tc_kernel<BBB_VARIANT_BBB>, grid, dim3(320), smem, st, a, stages);
-        if (e != cudaSuccess) return e;
-    }
-    (void)n_sm;
+    cudaFuncSetAttribute(gemm_tc_kernel<VARIANT, TF32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<VARIANT, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = launch_pdl(gemm_tc_kernel<VARIANT, TF32>, grid, dim3(320), smem, st, a, stages);
+    if (e != cudaSuccess) return e;
     e = cudaGetLastError();
     if (e == cudaSuccess) *n_launch += 1;
     return e;
+}
+
+inline cudaError_t launch_fwd_tc(TcArgs a, cudaStream_t st, int n_sm, int* n_launch) {
+    const Geom& g = a.g;
+    const bool tf32 = a.tf32 != 0;
+    a.planes = tc_planes(a.variant, a.sample);
+    a.n_tiles = tc_npad(g) / TC_BN;
+    a.k_blocks = tc_kpad(g, tf32) / tc_bk(tf32);
+    *n_launch = 0;
+    (void)n_sm;
+    const bool lrt = a.variant == BBB_VARIANT_LRT;
+    if (tf32) return lrt ? launch_fwd_tc_t<BBB_VARIANT_LRT, true>(a, st, n_launch) : launch_fwd_tc_t<BBB_VARIANT_BBB, true>(a, st, n_launch);
+    return lrt ? launch_fwd_tc_t<BBB_VARIANT_LRT, false>(a, st, n_launch) : launch_fwd_tc_t<BBB_VARIANT_BBB, false>(a, st, n_launch);
 }
 
 }  // namespace bbb

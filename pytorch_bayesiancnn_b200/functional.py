@@ -267,12 +267,15 @@ def out_hw(h, w, kh, kw, conv):
 _TC_K_MAX = 8192          # the gather kernel keeps an 8-byte table entry per reduction index in shared memory
 
 
+_tc_math = L.MATH_BF16_TC          # operand type of the backward contractions (set per call by _backward_tc)
+
+
 def _tc_contract(x, w, conv):
     """Plain (mean-only, bias-free) conv2d / linear of fp32 `x` with the fp32 tensor `w` on the tcgen05 layer kernel
-    (bf16 operands, fp32 TMEM accumulators): the engine's forward with sample=0 and no KL."""
+    (bf16 or tf32 operands like the layer's forward, fp32 TMEM accumulators): the engine's forward with sample=0, no KL."""
     lib = L.lib()
     x, w = x.contiguous(), w.contiguous()
-    d = make_desc(tuple(x.shape), tuple(w.shape), conv, L.VARIANT_BBB, False, False, 0.0, 1.0, L.MATH_BF16_TC)
+    d = make_desc(tuple(x.shape), tuple(w.shape), conv, L.VARIANT_BBB, False, False, 0.0, 1.0, _tc_math)
     if conv is None:
         y = torch.empty(x.shape[0], w.shape[0], dtype=torch.float32, device=x.device)
         fn = lib.bbb_linear_forward
@@ -330,7 +333,7 @@ def _tc_wgrad(x, g, conv, w_shape):
 
 
 def _tc_backward_ok(cfg):
-    return cfg["math"] in (L.MATH_BF16_TC, L.MATH_AUTO) and os.environ.get("BBB_B200_BWD", "tc") != "simt"
+    return cfg["math"] in (L.MATH_BF16_TC, L.MATH_AUTO, L.MATH_TF32_TC) and os.environ.get("BBB_B200_BWD", "tc") != "simt"
 
 
 # --------------------------------------------------------------------------- #
@@ -464,6 +467,8 @@ class BayesLayerFn(torch.autograd.Function):
         cfg = ctx.cfg
         conv, variant, sample = cfg["conv"], cfg["variant"], cfg["sample"]
         dev = x.device
+        global _tc_math
+        _tc_math = L.MATH_TF32_TC if cfg["math"] == L.MATH_TF32_TC else L.MATH_BF16_TC     # same operand type as the forward
         seed, stream_id, base = ctx.noise
         if base is not None:
             stream_id = int(stream_id) + int(base.item())

@@ -9,7 +9,7 @@ models/BayesianModels/*.py import and train unchanged.  The bodies are new: one
 fused CUDA kernel per forward (through the C ABI), KL computed in that kernel.
 
 Engine knobs ride on ``set_flag`` (never on the constructor):
-  math           'fp32' | 'bf16' | 'auto'   arithmetic path (default from $BBB_B200_MATH or 'auto': the tcgen05 tensor-core
+  math           'fp32' | 'bf16' | 'tf32' | 'auto'   arithmetic path (default from $BBB_B200_MATH or 'auto': the tcgen05 tensor-core
                                             path wherever the shape fits a UMMA tile, IEEE-fp32 CUDA cores otherwise;
                                             'fp32' forces the exact-arithmetic kernels everywhere)
   kl_convention  'reference' | 'textbook'   default 'reference' = the formula as executed
