@@ -425,7 +425,7 @@ def run_ours(args):
         ts.close()
 
     if rank == 0:
-        dt = "f32" if args.math == "fp32" else "bf16 operands, f32 accumulate"
+        dt = {"fp32": "f32", "tf32": "tf32 operands, f32 accumulate"}.get(args.math, "bf16 operands, f32 accumulate")
         out = {
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,

@@ -68,8 +68,8 @@ def test_tf32_alexnet_layer_shapes_b512(dev):
 
 
 def test_tf32_model_cases_external_eps(golden_models, dev):
-    """Whole models layer by layer on tf32 operands: the per-layer roundings compound over 5-8 layers, so the whole-model
-    bar is 2.5e-3 (the per-layer bar stays 1e-3 above; bf16 chains measure 4-8e-3 on the same cases)."""
+    """Whole models layer by layer on tf32 operands: 1e-3 on the logits of the whole model too (measured 4.3-6.7e-4; bf16
+    chains measure 4-8e-3 on the same cases)."""
     import pytorch_bayesiancnn_b200 as bbb
     from pytorch_bayesiancnn_b200 import models as M
     from oracle import bbb_oracle as O
@@ -86,7 +86,7 @@ def test_tf32_model_cases_external_eps(golden_models, dev):
             logits, kl = net(c["x"].to(dev))
         e = scale_err(logits, c["logits"])
         print(name, "tf32 whole-model scale err", e)
-        assert e < 2.5e-3, (name, e)
+        assert e < TF32_TOL, (name, e)
         assert abs(float(kl) - float(c["kl"])) <= KL_TOL * abs(float(c["kl"])), (name, float(kl), float(c["kl"]))
 
 
