@@ -702,18 +702,6 @@ inline cudaError_t launch_fwd_tc_t(TcArgs a, cudaStream_t st, int* n_launch) {
         const size_t per_sm = 228 * 1024;
         if (!TF32 && 2 * (smem + xs_elems * 4 + 1024) > per_sm && 2 * ((smem + xs_elems * 2 + 127) / 128 * 128 + 1024) <= per_sm) a.stage_x = 2;
         smem += xs_elems * (a.stage_x == 2 ? 2 : 4);
-    } else {
-        // Mid-size maps (BBB3Conv3FC conv2/conv3: 58 / 88 KB of fp32 per tile): every staged element is read KH*KW times by
-        // the tile, so staging still pays -- as bf16 (tf32: fp32) with a shallower weight/A ring to make room.
-        static const bool big = [] { const char* e = getenv("BBB_B200_STAGE_BIG"); return !(e && e[0] == '0'); }();
-        const size_t xs_bytes = (xs_elems * (TF32 ? 4 : 2) + 127) / 128 * 128;
-        int st2 = stages;
-        while (st2 > 2 && 1023 + tiles_off + (size_t)st2 * tc_stage_bytes(a.planes) + xs_bytes > (size_t)TC_SMEM_LIMIT) --st2;
-        if (big && xs_bytes <= 96 * 1024 && 1023 + tiles_off + (size_t)st2 * tc_stage_bytes(a.planes) + xs_bytes <= (size_t)TC_SMEM_LIMIT) {
-            stages = st2;
-            a.stage_x = TF32 ? 1 : 2;
-            smem = 1023 + tiles_off + (size_t)stages * tc_stage_bytes(a.planes) + xs_bytes;
-        }
     }
     dim3 grid((g.M + TC_BM - 1) / TC_BM, a.n_tiles);
     cudaFuncSetAttribute(gemm_tc_kernel<VARIANT, TF32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
