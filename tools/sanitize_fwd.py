@@ -19,4 +19,9 @@ for variant in ("lrt", "bbb"):
     with torch.no_grad():
         y = layer(torch.randn(8, 64, 4, 4, device=dev))
     torch.cuda.synchronize()
+    layer.set_flag("math", "tf32")                     # and its tf32-operand instance
+    with torch.no_grad():
+        y = layer(torch.randn(8, 64, 4, 4, device=dev))
+    layer.set_flag("math", "bf16")
+    torch.cuda.synchronize()
     print(variant, "ok", float(out["kl"]), tuple(y.shape))
