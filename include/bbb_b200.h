@@ -253,6 +253,12 @@ const char* bbb_last_error(void);
 int32_t bbb_abi_version(void);
 /* Number of kernels this library has launched since load (all entry points). */
 uint64_t bbb_launch_count(void);
+/* Tile policy of the fused chain's tap-GEMM layers (bbb_layer_forward_fused), read at launch (= graph capture) time:
+ * 0 (default) = 128-column tiles only where the grid still covers most of the SMs (best latency of ONE step);
+ * 1 = 128-column tiles wherever Cout allows (fewer operand bytes per MAC; best throughput when several independent
+ * steps are in flight and fill the SMs a narrow grid leaves idle -- measured 63.8 -> 59.5 us per BBBAlexNet step
+ * with four steps in flight, 92 -> 97 us for a single step).  Returns the previous value. */
+int32_t bbb_set_wide_tiles(int32_t prefer_wide);
 
 #ifdef __cplusplus
 }

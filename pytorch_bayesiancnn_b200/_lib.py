@@ -31,7 +31,7 @@ SYMBOLS = (
     "bbb_kl_backward", "bbb_conv2d_backward", "bbb_linear_backward", "bbb_philox_normal_fill",
     "bbb_mc_combine", "bbb_noise_advance", "bbb_last_error", "bbb_abi_version", "bbb_launch_count",
     "bbb_mc_buffer_bytes", "bbb_mc_state_bytes", "bbb_mc_exchange",
-    "bbb_comm_alloc", "bbb_comm_free", "bbb_comm_export", "bbb_comm_import", "bbb_comm_unimport",
+    "bbb_comm_alloc", "bbb_comm_free", "bbb_comm_export", "bbb_comm_import", "bbb_comm_unimport", "bbb_set_wide_tiles",
 )
 MC_MOMENTS, MC_NORMALIZED = 1, 2
 
@@ -99,6 +99,8 @@ def _bind(lib):
     lib.bbb_last_error.restype = C.c_char_p
     lib.bbb_abi_version.argtypes = []
     lib.bbb_abi_version.restype = i32
+    lib.bbb_set_wide_tiles.argtypes = [C.c_int32]
+    lib.bbb_set_wide_tiles.restype = C.c_int32
     lib.bbb_launch_count.argtypes = []
     lib.bbb_launch_count.restype = u64
     return lib

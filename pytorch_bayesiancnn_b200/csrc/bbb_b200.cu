@@ -17,6 +17,7 @@ namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
+std::atomic<int> g_wide_tiles{0};   // bbb_set_wide_tiles
 long long* g_trace = nullptr;      // debug hook (bbb_debug_set_trace)
 long long* g_mcx_trace = nullptr;  // debug hook (bbb_debug_set_mcx_trace): handshake stamps of the exchange kernel
 // debug hook (bbb_debug_set_timeline): launch k of the instrumented kernels writes [first CTA entry, last CTA
@@ -304,7 +305,7 @@ int bbb_layer_forward_fused(const bbb_layer_desc* d, const void* x, const void* 
         a.in_pitch = in_pitch; a.trace = g_trace; a.fold = fold;
         a.tl_prep = tl_slot(!skip_prep, "tap_prep", g); a.tl_gemm = tl_slot(!prep_only, "tap_gemm", g);
         const char* why = "";
-        cudaError_t e = bbb::launch_fused(a, x, x_sq, st, &nl, &why, !skip_prep, !prep_only, sm_count());
+        cudaError_t e = bbb::launch_fused(a, x, x_sq, st, &nl, &why, !skip_prep, !prep_only, sm_count(), g_wide_tiles.load() != 0);
         if (e != cudaSuccess) return fail(BBB_E_CUDA, "fused tap-GEMM launch: %s %s", cudaGetErrorString(e), why);
     } else {
         return fail(BBB_E_INVALID, "bad in_layout %d", in_layout);
@@ -476,5 +477,6 @@ const char* bbb_debug_timeline_name(int k) { return (k >= 0 && k < g_tl_n) ? g_t
 const char* bbb_last_error(void) { return g_err; }
 int32_t bbb_abi_version(void) { return BBB_ABI_VERSION; }
 uint64_t bbb_launch_count(void) { return g_launches.load(); }
+int32_t bbb_set_wide_tiles(int32_t prefer_wide) { return g_wide_tiles.exchange(prefer_wide ? 1 : 0); }
 
 }  // extern "C"

@@ -621,19 +621,19 @@ inline bool fused_supported(const Geom& g, int pool) {
 }
 
 inline cudaError_t launch_fused(FusedArgs a, const void* x, const void* x_sq, cudaStream_t st, int* n_launch, const char** why,
-                                bool do_prep = true, bool do_gemm = true, int n_sm = 148) {
+                                bool do_prep = true, bool do_gemm = true, int n_sm = 148, bool prefer_wide = false) {
     const Geom& g = a.g;
     *n_launch = 0;
     a.planes = tc_planes(a.variant, a.sample);
     // tile width: 128 columns when Cout allows it and the grid still covers most of the machine (operand bytes per MAC,
-    // see tap_gemm_kernel), else 64.  BBB_B200_TAP_BN=64 forces the narrow tile (A/B measurements).
+    // see tap_gemm_kernel) -- or always when the caller keeps several steps in flight (bbb_set_wide_tiles) -- else 64.  BBB_B200_TAP_BN=64 forces the narrow tile (A/B measurements).
     const int psets = a.pool ? (g.OH / 2) * (g.OW / 2) : g.OHW;
     const int row_tiles = (g.B + TC_BM - 1) / TC_BM;
     int bn = 64;
     {
         static const int force = [] { const char* e = getenv("BBB_B200_TAP_BN"); return e ? atoi(e) : 0; }();
         const int ng128 = a.pool ? 32 : 128;
-        if (g.N % ng128 == 0 && (long)psets * (g.N / ng128) * row_tiles >= (long)n_sm * 6 / 10) bn = 128;
+        if (g.N % ng128 == 0 && (prefer_wide || (long)psets * (g.N / ng128) * row_tiles >= (long)n_sm * 6 / 10)) bn = 128;
         if (force == 64 || force == 128) bn = (force == 128 && g.N % ng128 == 0) ? 128 : 64;
     }
     a.ng = a.pool ? bn / 4 : bn;

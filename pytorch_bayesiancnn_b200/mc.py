@@ -256,6 +256,17 @@ class MCForward:
     def _capture(self, warmup: int = 2):
         from .graph import _STRIDE
         dev = self.dev
+        # several steps in flight: the tap-GEMM layers take their 128-column tiles wherever Cout allows (throughput over the
+        # latency of one step; the choice is made at launch = capture time, include/bbb_b200.h bbb_set_wide_tiles)
+        prev_wide = L.lib().bbb_set_wide_tiles(1 if self.inflight > 1 else 0)
+        try:
+            self._capture_graphs(warmup)
+        finally:
+            L.lib().bbb_set_wide_tiles(prev_wide)
+
+    def _capture_graphs(self, warmup):
+        from .graph import _STRIDE
+        dev = self.dev
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
