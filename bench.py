@@ -368,6 +368,15 @@ def run_ours(args):
         except Exception as e:                                    # a diagnostic, never the reason a bench run fails
             in_chain = [{"note": f"failed: {e}"[:200]}]
 
+    if roof is not None:
+        # the whole step against the sum of the per-layer rooflines: what fraction of the step time the
+        # algorithmic FLOPs / bytes of its six layers would need at the measured peaks
+        step_us = total_ms / args.steps * 1e3
+        fl = sum(algorithmic(r, args.variant, 2 if args.math != "fp32" else 4)[0] for r in layer_table(B * S_local, C))
+        roof["whole_step"] = {"step_us": step_us, "tflops": fl / (step_us * 1e-6) / 1e12,
+                              "frac_of_sum_of_layer_rooflines": roof["net_t_roof_us"] * S_local / step_us if "net_t_roof_us" in roof else None,
+                              "note": f"{infl} step(s) in flight; net_t_roof_us is per MC sample of the batch"}
+
     mc_batched = None
     if rank == 0 and world == 1 and args.config == "headline" and cfg["variant"] == "lrt" and args.mc_batch > 1:
         # configs[2] literally: S = 10 MC samples of the batch.  For LRT the samples differ only in the per-activation
