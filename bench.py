@@ -450,8 +450,10 @@ def run_ours(args):
                        "batch": B, "variant": cfg["variant"], "math": args.math, "mc_samples_total": S_total,
                        "parallelism": f"mc{world}", "steps_in_flight": infl, "exchange_overlapped": ovl,
                        "l2": f"no flush: inputs rotate through {n_dev_inputs} resident batches = {n_dev_inputs * in_bytes >> 20} MB > 126 MB L2",
-                       "launch": "one CUDA graph replay per step (noise advance, per-layer prep + GEMM kernels, KL sum, MC exchange "
-                                 "kernel over NVLink peer memory); one captured graph per resident input batch, read in place",
+                       "launch": ("two CUDA graph replays per step (layer chain: noise advance, per-layer prep + GEMM kernels; then the MC "
+                                  "exchange kernel over NVLink peer memory on its own stream, beside the next step's chain)" if ovl else
+                                  "one CUDA graph replay per step (noise advance, per-layer prep + GEMM kernels, MC exchange kernel over "
+                                  "NVLink peer memory)") + "; one captured graph per resident input batch, read in place",
                        "timing": f"median of {args.windows} windows of {args.steps} steps, each bracketed by barrier+synchronize, "
                                  f"CUDA events, max over ranks per window"},
             "windows_ms": {"min": min(wins), "median": total_ms, "max": max(wins), "n": len(wins)},
