@@ -217,8 +217,9 @@ int bbb_mc_combine(const float* logits, int32_t S, int32_t B, int32_t C,
  * The num_ens samples are sharded over `world` ranks (one process per GPU); this rank holds `S_local` of the
  * `S_total` samples' logits [S_local, B, C].  One kernel: per-(image, class) partials of the local samples
  * (the exact (max, sum-exp) pair of logmeanexp, + sum p / sum p^2 / sum logits with BBB_MC_MOMENTS) are stored straight
- * into every rank's receive buffer over NVLink (peer-mapped memory, below), per-CTA release flags are raised, the
- * peers' flags awaited, and the result finished locally in fixed rank order (bitwise identical on all ranks):
+ * into every rank's receive buffer over NVLink (peer-mapped memory, below) as 8-byte words {value, sequence number};
+ * the receiver polls each word until its tag matches (no fence, no flag; a lost peer is a counted time-out, never a
+ * hang) and the result is finished locally in fixed rank order (bitwise identical on all ranks):
  *   log_outputs [B,C] = logmeanexp_j log_softmax(logits_j)      kl_out = sum_j kl_j / S_total
  *   pred / epistemic / aleatoric [B,C], entropy [B]             (nullable; need BBB_MC_MOMENTS)
  *   head [4] = {nll*train_size + beta*kl, nll, accuracy, beta*kl}   (nullable; needs labels [B] int64)
