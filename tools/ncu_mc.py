@@ -6,6 +6,9 @@ import torch
 from pytorch_bayesiancnn_b200 import mc
 from bench import build_net
 dev = torch.device("cuda:0")
+from pytorch_bayesiancnn_b200 import _lib as L
+if os.environ.get("NCU_WIDE_TILES", "0") == "1":          # the tile policy of the in-flight engines (bbb_set_wide_tiles)
+    L.lib().bbb_set_wide_tiles(1)
 net = build_net(sys.argv[1] if len(sys.argv) > 1 else "lrt", 10, dev, "bf16")
 xs = [torch.randn(512, 3, 32, 32, device=dev) for _ in range(4)]
 eng = mc.MCForward(net, xs[0], 1, seed=1, graph=False)
