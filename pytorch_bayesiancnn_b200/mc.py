@@ -144,8 +144,6 @@ class MCForward:
         if fold and len(self.ids) > 1 and all_lrt:
             self.fold = (self.B, self.world << 40)
             self.fold_steps = fused.plan(kids, (len(self.ids) * self.B,) + tuple(example_x.shape[1:]), self.fold)
-        # an all-LRT net that runs as a fused chain: its weight preps do not depend on the step's noise base
-        self._lrt_chain = all_lrt and (self.fold_steps is not None or fused.plan(kids, tuple(example_x.shape)) is not None)
         self.graph, self.graphs = None, []
         self.result_stream = None                 # overlap mode: the stream the results are complete on
         self.replays = 0
