@@ -33,6 +33,20 @@ def test_library_exports_every_declared_symbol(built):
     assert ctypes.sizeof(_lib.LayerDesc) == 4 * 26 + 8
 
 
+def test_header_enums_match_the_python_mirror_and_tile_policy_is_host_only(built):
+    """The enum values ctypes passes are the header's; bbb_set_wide_tiles is a host-side switch (no GPU needed)."""
+    from pytorch_bayesiancnn_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "bbb_b200.h")).read()
+    val = lambda name: int(re.search(name + r"\s*=\s*(-?\d+)", hdr).group(1))
+    assert (val("BBB_MATH_FP32"), val("BBB_MATH_BF16_TC"), val("BBB_MATH_AUTO"), val("BBB_MATH_TF32_TC")) == \
+        (_lib.MATH_FP32, _lib.MATH_BF16_TC, _lib.MATH_AUTO, _lib.MATH_TF32_TC)
+    assert (val("BBB_MC_MOMENTS"), val("BBB_MC_NORMALIZED")) == (_lib.MC_MOMENTS, _lib.MC_NORMALIZED)
+    assert set(_lib.MATH_BY_NAME) == {"fp32", "bf16", "tf32", "auto"}
+    lib = _lib.lib()
+    prev = lib.bbb_set_wide_tiles(1)
+    assert lib.bbb_set_wide_tiles(prev) == 1 and lib.bbb_set_wide_tiles(prev) == prev
+
+
 def test_invalid_calls_return_error_codes_without_gpu(built):
     from pytorch_bayesiancnn_b200 import _lib
     lib = _lib.lib()
